@@ -1,0 +1,206 @@
+"""Base-graph container and dataset loading for the GLASS hot path.
+
+Mirrors the *interface* of the reference's datasets.py (BaseGraph :11-101, load_dataset :103-229)
+for the parts the hot path consumes: x / edge_index / edge_attr / pos / y / mask, setOneFeature,
+setNodeIdFeature, setDegreeFeature, get_split, to().  One-time host preprocessing; not accelerated.
+
+Data sources
+  * "density", "cut_ratio", "coreness", "component": the reference's shipped synthetic datasets,
+    re-encoded as integer arrays in data/<name>.npz by scripts/convert_shipped_datasets.py
+    (datasets.py:105-125 reads the same content from a networkx pickle).
+  * "ppi_bp_shaped", "em_user_shaped", "stress[_small]": seeded synthetic graphs of the shapes
+    BASELINE.json names (the real ppi_bp / em_user data and embeddings are not shipped).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+_DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+SHIPPED = ("density", "cut_ratio", "coreness", "component")
+
+
+def coalesce_undirected(edge: torch.Tensor, weight: torch.Tensor, n_node: int):
+    """Symmetrise then sort by (row, col) and merge duplicates by summing weights.
+
+    Same result as PyG ``to_undirected(edge_index, edge_attr)`` used at datasets.py:68-71.
+    """
+    row = torch.cat((edge[0], edge[1]))
+    col = torch.cat((edge[1], edge[0]))
+    w = torch.cat((weight, weight))
+    key, inv = torch.unique(row * n_node + col, sorted=True, return_inverse=True)
+    out_w = torch.zeros(key.numel(), dtype=weight.dtype).index_add_(0, inv, w)
+    return torch.stack((torch.div(key, n_node, rounding_mode="floor"), key % n_node)), out_w
+
+
+def _is_undirected(edge: torch.Tensor, n_node: int) -> bool:
+    key = torch.unique(edge[0] * n_node + edge[1])
+    key_t = torch.unique(edge[1] * n_node + edge[0])
+    return key.numel() == edge.shape[1] and torch.equal(key, key_t)
+
+
+class BaseGraph:
+    """x [N,1,F] int64 ids, edge_index [2,nnz] int64, edge_attr [nnz] fp32, pos [S,Lmax] (-1 pad),
+    y [S], mask [S] in {0: train, 1: valid, 2: test} -- the layout of datasets.py:14-21."""
+
+    def __init__(self, x, edge_index, edge_weight, subG_node, subG_label, mask):
+        self.x = x
+        self.edge_index = edge_index
+        self.edge_attr = edge_weight
+        self.pos = subG_node
+        self.y = subG_label
+        self.mask = mask
+        self.to_undirected()
+
+    @property
+    def num_nodes(self) -> int:
+        return self.x.shape[0]
+
+    def to_undirected(self):
+        n = self.x.shape[0]
+        if not _is_undirected(self.edge_index, n):
+            self.edge_index, self.edge_attr = coalesce_undirected(self.edge_index, self.edge_attr, n)
+
+    def _degree(self):
+        deg = torch.zeros(self.x.shape[0], dtype=self.edge_attr.dtype)
+        return deg.index_add_(0, self.edge_index[0].cpu(), self.edge_attr.cpu()).to(torch.int64)
+
+    def setDegreeFeature(self, mod: int = 1):
+        deg = torch.div(self._degree(), mod, rounding_mode="floor")
+        self.x = torch.unique(deg, return_inverse=True)[1].reshape(self.x.shape[0], 1, -1)
+
+    def setOneFeature(self):
+        self.x = torch.ones((self.x.shape[0], 1, 1), dtype=torch.int64)
+
+    def setNodeIdFeature(self):
+        self.x = torch.arange(self.x.shape[0], dtype=torch.int64).reshape(self.x.shape[0], 1, -1)
+
+    def get_split(self, split: str):
+        sel = self.mask == {"train": 0, "valid": 1, "test": 2}[split]
+        return self.x, self.edge_index, self.edge_attr, self.pos[sel], self.y[sel]
+
+    def to(self, device):
+        for name in ("x", "edge_index", "edge_attr", "pos", "y", "mask"):
+            setattr(self, name, getattr(self, name).to(device))
+        return self
+
+
+def load_edges(name: str) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Undirected, (row, col)-sorted edge_index / unit weights / node count of a shipped dataset."""
+    d = np.load(os.path.join(_DATA_DIR, f"{name}.npz"))
+    n = int(d["n_node"])
+    e = torch.from_numpy(d["edge"].astype(np.int64))
+    ei, ew = coalesce_undirected(e, torch.ones(e.shape[1]), n)
+    return ei, ew, n
+
+
+def _pad_rows(rows, fill=-1) -> torch.Tensor:
+    lmax = max(len(r) for r in rows)
+    out = torch.full((len(rows), lmax), fill, dtype=torch.int64)
+    for i, r in enumerate(rows):
+        out[i, :len(r)] = torch.as_tensor(r, dtype=torch.int64)
+    return out
+
+
+def uniform_edges(n: int, n_und: int, seed: int) -> torch.Tensor:
+    """n_und distinct undirected edges without self loops, sampled uniformly (numpy PCG64, seeded)."""
+    g = np.random.default_rng(seed)
+    got = np.zeros(0, dtype=np.int64)
+    while got.shape[0] < n_und:
+        m = int((n_und - got.shape[0]) * 1.1) + 1024
+        a, b = g.integers(0, n, m), g.integers(0, n, m)
+        keep = a != b
+        lo, hi = np.minimum(a, b)[keep], np.maximum(a, b)[keep]
+        got = np.unique(np.concatenate((got, lo * n + hi)))
+    got = g.permutation(got)[:n_und]
+    return torch.from_numpy(np.stack((got // n, got % n)))
+
+
+def powerlaw_edges(n: int, n_und: int, seed: int, alpha: float = 2.1) -> torch.Tensor:
+    """Chung-Lu style skewed graph: endpoints drawn with probability ~ rank^(-1/(alpha-1))."""
+    g = np.random.default_rng(seed)
+    wgt = np.arange(1, n + 1, dtype=np.float64) ** (-1.0 / (alpha - 1.0))
+    cdf = np.cumsum(wgt)
+    cdf /= cdf[-1]
+    perm = g.permutation(n)  # hubs scattered over the id range
+    got = np.zeros(0, dtype=np.int64)
+    while got.shape[0] < n_und:
+        m = int((n_und - got.shape[0]) * 1.3) + 1024
+        a = perm[np.searchsorted(cdf, g.random(m))]
+        b = perm[np.searchsorted(cdf, g.random(m))]
+        keep = a != b
+        lo, hi = np.minimum(a, b)[keep], np.maximum(a, b)[keep]
+        got = np.unique(np.concatenate((got, lo * n + hi)))
+    got = g.permutation(got)[:n_und]
+    return torch.from_numpy(np.stack((got // n, got % n)))
+
+
+def _random_subgraphs(n, count, mean_len, std_len, min_len, seed):
+    g = np.random.default_rng(seed)
+    rows = []
+    for _ in range(count):
+        if std_len is None:
+            k = int(g.poisson(mean_len))
+        else:
+            k = int(round(g.normal(mean_len, std_len)))
+        k = min(max(k, min_len), n)
+        rows.append(g.choice(n, size=k, replace=False))
+    return rows
+
+
+_SHAPES = {
+    # name: nodes, undirected edges, subgraphs, mean/std/min size, classes (2 => binary float labels)
+    "ppi_bp_shaped": dict(n=17080, e=316951, s=1591, mean=10, std=None, lmin=2, classes=6),
+    "em_user_shaped": dict(n=57333, e=4573417, s=324, mean=155, std=100, lmin=2, classes=2),
+    "em_user_shaped_powerlaw": dict(n=57333, e=4573417, s=324, mean=155, std=100, lmin=2, classes=2, gen="powerlaw"),
+    "stress": dict(n=2_000_000, e=100_000_000, s=512, mean=64, std=None, lmin=2, classes=2, gen="powerlaw"),
+    "stress_small": dict(n=200_000, e=5_000_000, s=256, mean=64, std=None, lmin=2, classes=2, gen="powerlaw"),
+}
+
+
+def synthetic_graph(name: str, seed: int = 0) -> "BaseGraph":
+    """Seeded synthetic stand-ins for the datasets that are not shipped."""
+    s = _SHAPES[name]
+    gen = powerlaw_edges if s.get("gen") == "powerlaw" else uniform_edges
+    e = gen(s["n"], s["e"], seed)
+    rows = _random_subgraphs(s["n"], s["s"], s["mean"], s["std"], s["lmin"], seed + 1)
+    g = np.random.default_rng(seed + 2)
+    label = torch.from_numpy(g.integers(0, s["classes"], s["s"]))
+    n_trn = int(0.8 * s["s"])
+    n_val = int(0.1 * s["s"])
+    mask = torch.cat((torch.zeros(n_trn, dtype=torch.int64), torch.ones(n_val, dtype=torch.int64),
+                      2 * torch.ones(s["s"] - n_trn - n_val, dtype=torch.int64)))
+    return BaseGraph(torch.empty((s["n"], 1, 0)), e, torch.ones(e.shape[1]), _pad_rows(rows),
+                     label.to(torch.float) if s["classes"] == 2 else label, mask)
+
+
+def synthetic_embedding(n: int, dim: int, seed: int = 0, std: float = 2.0) -> torch.Tensor:
+    """Stand-in for the missing Emb/<dataset>_64.pt (the shipped hpo tables have std 1.8-2.2)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, dim, generator=g) * std
+
+
+def load_dataset(name: str, seed: Optional[int] = None) -> "BaseGraph":
+    """datasets.py:103-126 for the shipped synthetic sets; seeded generators for the *_shaped ones.
+
+    For shipped sets the split permutation is drawn from torch's global RNG exactly as the
+    reference does (datasets.py:118-123), so ``--use_seed`` reproduces the reference's splits.
+    """
+    if name in SHIPPED:
+        d = np.load(os.path.join(_DATA_DIR, f"{name}.npz"))
+        n = int(d["n_node"])
+        pad = torch.from_numpy(d["subG_pad"].astype(np.int64))
+        label = torch.from_numpy(d["label"].astype(np.int64))
+        cnt = pad.shape[0]
+        mask = torch.cat((torch.zeros(cnt - cnt // 2, dtype=torch.int64),
+                          torch.ones(cnt // 4, dtype=torch.int64),
+                          2 * torch.ones(cnt // 2 - cnt // 4, dtype=torch.int64)))
+        mask = mask[torch.randperm(mask.shape[0])]
+        e = torch.from_numpy(d["edge"].astype(np.int64))
+        return BaseGraph(torch.empty((n, 1, 0)), e, torch.ones(e.shape[1]), pad, label, mask)
+    if name in _SHAPES:
+        return synthetic_graph(name, 0 if seed is None else seed)
+    raise NotImplementedError(name)

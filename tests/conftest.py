@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "needs_reference: needs /root/reference (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    has_ref = os.path.isdir(os.environ.get("GLASS_REFERENCE", "/root/reference"))
+    skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    for item in items:
+        if "needs_reference" in item.keywords and not has_ref:
+            item.add_marker(skip_ref)
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
