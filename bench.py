@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the GLASS labeled message-passing hot path on B200 (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload em_user_shaped] [--impl reference]
+
+A "step" is one training iteration of impl/train.py:10-16 (labels z, forward, loss, backward, optimizer)
+over one label batch on the whole base graph.  Default workload: the em_user-shaped synthetic graph with
+config/em_user.yml hyper-parameters (BASELINE.json configs[3], the roofline config).  Prints ONE JSON line
+(contract in the task statement): device-timed `value`, host-buffer `e2e`, the SpMM `roofline`, and the
+CPU `cpu_baseline` (oracle port of the reference modules, timed on this box's host cores).
+`--impl reference` times that CPU port alone with the same metric/config keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHIPPED = ("density", "cut_ratio", "coreness", "component")
+
+
+# ------------------------------------------------------------------------------------------ workload
+def make_workload(name: str, seed: int = 0):
+    """Graph, hyper-parameters, node ids, (synthetic) embedding table and the train split, on the host."""
+    from glass_b200 import datasets, run
+    torch.manual_seed(seed)
+    g = datasets.load_dataset(name)
+    params = run.load_params(name)
+    loss_fn, out_dim, score_fn, y = run.task_of(g.y)
+    g.y = y
+    if name in SHIPPED:
+        g.setOneFeature()                      # --use_one (README.md:50-53 commands for synthetic sets)
+        table = None
+    else:
+        g.setNodeIdFeature()                   # --use_nodeid with a seeded stand-in for Emb/<name>_64.pt
+        table = datasets.synthetic_embedding(g.num_nodes, params["hidden_dim"], seed)
+    trn = g.get_split("train")
+    return dict(name=name, g=g, params=params, loss_fn=loss_fn, out_dim=out_dim, table=table,
+                trn_pos=trn[3], trn_y=trn[4], max_deg=int(g.x.max()))
+
+
+def batches_for(wl, n_steps: int, rank: int, world: int, seed: int = 0):
+    """Host (pos, y) batches: one shared seeded order, rank r takes batches r, r+P, ... of every epoch."""
+    from glass_b200.dist import shard_batches, shared_permutation
+    bs = wl["params"]["batch_size"]
+    n_trn = wl["trn_pos"].shape[0]
+    per_epoch = n_trn // bs                    # drop_last=True like GLASSTest.py:106-116
+    out, epoch = [], 0
+    while len(out) < n_steps:
+        perm = shared_permutation(n_trn, seed, epoch)
+        for b in shard_batches(per_epoch, rank, world):
+            idx = perm[b * bs:(b + 1) * bs]
+            out.append((wl["trn_pos"][idx].contiguous(), wl["trn_y"][idx].contiguous()))
+            if len(out) == n_steps:
+                break
+        epoch += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.stop = index, [], set(), False
+        self.max_mhz, self.thread = None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def loop():
+                while not self.stop:
+                    try:
+                        self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, nm in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.thread:
+            self.thread.join(timeout=1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ CPU port (reference arm)
+def cpu_port_steps(wl, n_steps: int, warmup: int, train: bool = True):
+    """Times the oracle port of the reference modules (same ATen op sequence as impl/models.py on CPU)."""
+    from oracle import glass_oracle as O
+    p = wl["params"]
+    g = wl["g"]
+    cfg = O.GlassConfig(hidden_dim=p["hidden_dim"], conv_layer=p["conv_layer"], aggr=p["aggr"], z_ratio=p["z_ratio"],
+                        dropout=p["dropout"], pool=p["pool"], jk=True, activation="elu", out_dim=wl["out_dim"])
+    sd = O.init_state_dict(cfg, wl["max_deg"] + 1, seed=0, pretrained=wl["table"])
+    model = O.OracleModel(cfg, sd)
+    opt = torch.optim.Adam(model.params, lr=p["lr"])
+    loss_fn = O.loss_fn_for(wl["out_dim"] == 1 and g.y.dtype == torch.float32)
+    batches = batches_for(wl, n_steps + warmup, 0, 1)
+    for pos, y in batches[:warmup]:
+        model.step(opt, g.x, g.edge_index, g.edge_attr, pos, y, loss_fn, training=train)
+    t0 = time.perf_counter()
+    for pos, y in batches[warmup:]:
+        model.step(opt, g.x, g.edge_index, g.edge_attr, pos, y, loss_fn, training=train)
+    dt = time.perf_counter() - t0
+    return p["batch_size"] * n_steps / dt, dt / n_steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    wl = make_workload(args.workload)
+    value, per_step = cpu_port_steps(wl, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = base_line(args, wl, value, per_step * 1e3)
+    line.update(impl="reference", n_gpus=args.gpus, dtype="f32",
+                cpu_baseline={"value": value, "unit": "subgraphs/s", "cores": cores, "kind": "port",
+                              "sample": f"{args.steps} train steps of batch {wl['params']['batch_size']} on the full "
+                                        f"{wl['name']} graph (oracle port of impl/models.py; /root/reference is not on this box)"},
+                e2e={"value": value, "unit": "subgraphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def base_line(args, wl, value, ms_per_step):
+    p = wl["params"]
+    g = wl["g"]
+    return {"metric": "subgraphs/s (train)", "value": value, "unit": "subgraphs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "nodes": g.num_nodes, "nnz": int(g.edge_index.shape[1]),
+                       "hidden_dim": p["hidden_dim"], "conv_layer": p["conv_layer"], "aggr": p["aggr"],
+                       "pool": p["pool"], "batch_size_per_gpu": p["batch_size"], "dropout": p["dropout"],
+                       "z_ratio": p["z_ratio"], "subgraph_pad": int(wl["trn_pos"].shape[1]),
+                       "parallelism": f"label-batch dp{args.gpus}",
+                       "l2": "flushed (256 MiB write) between isolated SpMM timings; whole-step working set "
+                             "(A, A^T, activations) exceeds L2"}}
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def spmm_roofline(adj, h: int, reps: int = 20):
+    """Isolated SpMM launches, L2 flushed before each, CUDA events on the launching stream."""
+    from glass_b200 import ops
+    dev = adj.col.device
+    x = torch.randn(adj.n, h, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for _ in range(3):
+        ops.spmm(adj, x)
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        ops.spmm(adj, x)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    avg = sum(ms) / len(ms)
+    algo = 4 * (adj.n + 1) + 8 * adj.nnz + 8 * adj.n * h
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo / (avg * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmm_traffic.json")) as f:
+            t = json.load(f)
+            if t.get("nnz") == adj.nnz and t.get("h") == h:
+                traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": "k_spmm (glass_spmm_csr)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": algo, "us_per_launch": avg * 1e3,
+            "us_min": ms[0] * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+            "gather_bytes_l2": 4 * h * adj.nnz}
+
+
+def run_product(args):
+    import torch.distributed as dist
+
+    from glass_b200 import build as _build
+    _build.build()
+    from glass_b200 import ops, run, train, utils
+    from glass_b200.dist import FlatGradAllReduce
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = make_workload(args.workload)
+    p, g = wl["params"], wl["g"]
+    torch.manual_seed(0)
+    model = run.build_model(p["hidden_dim"], p["conv_layer"], p["dropout"], 1, p["pool"], p["z_ratio"], p["aggr"],
+                            wl["max_deg"], wl["out_dim"], pretrained=wl["table"], device=dev)
+    x, ei, ew = g.x.to(dev), g.edge_index.to(dev), g.edge_attr.to(dev)
+    loss_fn = wl["loss_fn"]
+    opt = torch.optim.Adam(model.parameters(), lr=p["lr"])
+    flat = FlatGradAllReduce(model.parameters())
+    n_total = args.warmup + args.steps
+    host_batches = [(pos.pin_memory(), y.pin_memory()) for pos, y in batches_for(wl, n_total, rank, world)]
+    dev_batches = [(pos.to(dev), y.to(dev)) for pos, y in host_batches]
+
+    def step(pos, y):
+        z = utils.MaxZOZ(x, pos)
+        flat.zero()
+        loss = loss_fn(model(x, ei, ew, pos, z, id=0), y)
+        loss.backward()
+        flat.allreduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed value: inputs resident in HBM
+    model.train()
+    for pos, y in dev_batches[:args.warmup]:
+        step(pos, y)
+    barrier()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for pos, y in dev_batches[args.warmup:]:
+            step(pos, y)
+        e1.record()
+        barrier()
+    launches = ops.launch_count()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    bs = p["batch_size"]
+    value = bs * args.steps * world / (ms * 1e-3)
+
+    # ---- e2e: public train API, host buffers -> device every step, loss read back every step
+    class HostLoader:
+        def __iter__(self):
+            for pos, y in host_batches[args.warmup:]:
+                pd, yd = pos.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                yield x, ei, ew, pd, utils.MaxZOZ(x, pd), yd
+
+        def __len__(self):
+            return args.steps
+
+    class Opt:  # train.train calls optimizer.zero_grad()/step(); route them to the flat buffer + allreduce
+        def zero_grad(self):
+            flat.zero()
+
+        def step(self):
+            flat.allreduce_mean()
+            opt.step()
+
+    barrier()
+    t0 = time.perf_counter()
+    train.train(Opt(), model, HostLoader(), loss_fn)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = bs * args.steps * world / float(e2e_s)
+    h2d = host_batches[0][0].numel() * 8 + host_batches[0][1].numel() * host_batches[0][1].element_size()
+
+    if rank == 0:
+        line = base_line(args, wl, value, ms / args.steps)
+        line["e2e"] = {"value": e2e_value, "unit": "subgraphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "api": "glass_b200.train.train"}
+        line["gpu_launches"] = launches
+        line["clocks"] = clocks.summary()
+        adj = model.conv.convs[0].adj
+        line["roofline"] = spmm_roofline(adj, p["hidden_dim"])
+        # inference throughput of the same model / batches (impl/train.py:20-34 forward only)
+        model.eval()
+        with torch.no_grad():
+            for pos, y in dev_batches[:args.warmup]:
+                model(x, ei, ew, pos, utils.MaxZOZ(x, pos))
+            torch.cuda.synchronize()
+            e0.record()
+            for pos, y in dev_batches[args.warmup:]:
+                model(x, ei, ew, pos, utils.MaxZOZ(x, pos))
+            e1.record()
+            torch.cuda.synchronize()
+        line["infer"] = {"value": bs * args.steps / (e0.elapsed_time(e1) * 1e-3), "unit": "subgraphs/s",
+                         "n_gpus": 1}
+        if world == 1 and not args.no_cpu_baseline:
+            v, per = cpu_port_steps(wl, args.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "subgraphs/s", "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": f"{args.cpu_steps} train steps (after 1 warm-up) of batch {bs} on the full "
+                                              f"{wl['name']} graph, oracle port of impl/models.py",
+                                    "ms_per_step": per * 1e3}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="glass_b200", choices=["glass_b200", "reference"])
+    ap.add_argument("--workload", default="em_user_shaped")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,59 @@
+// Shared helpers for the glass_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/glass_b200.h"
+
+namespace glass {
+
+void set_error(const char* fmt, ...);
+
+#define GLASS_CHECK_ARG(cond, ...)                 \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::glass::set_error(__VA_ARGS__);       \
+            return GLASS_ERR_BAD_ARG;              \
+        }                                          \
+    } while (0)
+
+#define GLASS_CUDA(call)                                                                      \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ::glass::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return GLASS_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define GLASS_LAUNCH_CHECK() GLASS_CUDA(cudaPeekAtLastError())
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached per process
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == GLASS_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == GLASS_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+// derivative expressed through the POST-activation value (ELU alpha = 1: d/dx = y + 1 for x <= 0)
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    if (act == GLASS_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (act == GLASS_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+    return 1.f;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace glass

@@ -1,0 +1,283 @@
+"""Drop-in modules for the GLASS hot path, same API as the reference's impl/models.py.
+
+buildAdj (:83), GLASSConv (:114), EmbZGConv (:177), PoolModule / AddPool / MaxPool / MeanPool /
+SizePool (:275-319) and GLASS (:322) keep their constructor signatures, forward signatures, parameter
+names (identical ``state_dict`` keys) and parameter creation order (identical seeded initialisation),
+but every tensor op runs in the hand-written sm_100a kernels of libglass_b200.so via glass_b200.ops.
+There is no torch.sparse / PyG / CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import ACT_ELU, ACT_NONE, ACT_RELU
+from .utils import pad2batch
+
+
+def _act_id(activation) -> int:
+    """Map the activation *module* the reference passes (GLASSTest.py:143 nn.ELU(inplace=True); default
+    nn.ReLU, impl/models.py:125, 192) to the fused-kernel enum.  Anything else is not accelerated."""
+    if activation is None or isinstance(activation, nn.Identity):
+        return ACT_NONE
+    if isinstance(activation, nn.ReLU):
+        return ACT_RELU
+    if isinstance(activation, nn.ELU) and activation.alpha == 1.0:
+        return ACT_ELU
+    raise NotImplementedError(f"activation {activation!r} is not supported by the fused GLASS kernels")
+
+
+class GraphNorm(nn.Module):
+    """Parameter-compatible stand-in for PyG 1.7.2 ``GraphNorm(in_channels)`` (weight, bias, mean_scale
+    registered in that order, ones/zeros/ones).  Only whole-graph normalisation (batch=None), which is
+    the only way the GLASS path calls it (impl/models.py:165, 249, 257, 266)."""
+
+    def __init__(self, in_channels: int, eps: float = 1e-5):
+        super().__init__()
+        self.in_channels = in_channels
+        self.eps = eps
+        self.weight = nn.Parameter(torch.empty(in_channels))
+        self.bias = nn.Parameter(torch.empty(in_channels))
+        self.mean_scale = nn.Parameter(torch.empty(in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.ones_(self.weight)
+        nn.init.zeros_(self.bias)
+        nn.init.ones_(self.mean_scale)
+
+    def forward(self, x, batch=None, act: int = ACT_NONE, p: float = 0.0, training: bool = False):
+        if batch is not None:
+            raise NotImplementedError("only whole-graph GraphNorm (batch=None) is on the GLASS path")
+        return ops.graph_norm(x, self.weight, self.bias, self.mean_scale, self.eps, act, p, training)
+
+
+_adj_cache = {}
+
+
+def buildAdj(edge_index, edge_weight, n_node: int, aggr: str):
+    """impl/models.py:83-111.  Returns a CSRAdj (CSR + transposed CSR, normalised for ``aggr``) that
+    supports ``adj @ x``.  Identical (edge_index, edge_weight, n_node, aggr) inputs share one CSR so
+    the L layers of a model do not each rebuild the same matrix."""
+    if aggr not in ("mean", "sum", "gcn"):
+        raise NotImplementedError
+    key = (edge_index.data_ptr(), edge_weight.data_ptr(), tuple(edge_index.shape), int(n_node), aggr,
+           edge_index._version, edge_weight._version, str(edge_index.device))
+    hit = _adj_cache.get(key)
+    if hit is not None and hit[0]() is edge_index and hit[1]() is edge_weight:
+        return hit[2]
+    adj = ops.build_csr(edge_index, edge_weight, n_node, aggr)
+    import weakref
+    if len(_adj_cache) > 16:
+        _adj_cache.clear()
+    _adj_cache[key] = (weakref.ref(edge_index), weakref.ref(edge_weight), adj)
+    return adj
+
+
+def _mask_u8(mask: torch.Tensor) -> torch.Tensor:
+    """bool [N,1] (reference convention, impl/models.py:242-246) or uint8 [N] -> uint8 [N] without a copy."""
+    m = mask.reshape(-1)
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    return m
+
+
+class GLASSConv(nn.Module):
+    """impl/models.py:114-174: label-mixed transform -> adj @ x -> GraphNorm -> dropout -> [x | x_] ->
+    label-mixed combine.  Four kernels: pair GEMM (+act+mix), SpMM, GraphNorm(+dropout), pair GEMM over
+    the virtual concat (+mix)."""
+
+    def __init__(self, in_channels: int, out_channels: int, activation=nn.ReLU(inplace=True), aggr="mean",
+                 z_ratio=0.8, dropout=0.2):
+        super().__init__()
+        self.trans_fns = nn.ModuleList([nn.Linear(in_channels, out_channels), nn.Linear(in_channels, out_channels)])
+        self.comb_fns = nn.ModuleList([nn.Linear(in_channels + out_channels, out_channels),
+                                       nn.Linear(in_channels + out_channels, out_channels)])
+        self.adj = None
+        self.activation = activation
+        self.aggr = aggr
+        self.gn = GraphNorm(out_channels)
+        self.z_ratio = z_ratio
+        self.reset_parameters()
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for lin in self.trans_fns:
+            lin.reset_parameters()
+        for lin in self.comb_fns:
+            lin.reset_parameters()
+        self.gn.reset_parameters()
+
+    def forward(self, x_, edge_index, edge_weight, mask):
+        if self.adj is None:  # cached on first use, like impl/models.py:154-156
+            self.adj = buildAdj(edge_index, edge_weight, x_.shape[0], self.aggr)
+        m = _mask_u8(mask)
+        t0, t1 = self.trans_fns
+        x = ops.pair_linear_mix(x_, None, t0.weight, t0.bias, t1.weight, t1.bias, m, self.z_ratio,
+                                _act_id(self.activation))                                   # :158-162
+        x = ops.spmm(self.adj, x)                                                           # :164
+        x = self.gn(x, p=self.dropout, training=self.training)                              # :165-166
+        c0, c1 = self.comb_fns
+        return ops.pair_linear_mix(x, x_, c0.weight, c0.bias, c1.weight, c1.bias, m, self.z_ratio,
+                                   ACT_NONE)                                                # :167-173
+
+
+class EmbZGConv(nn.Module):
+    """impl/models.py:177-272: embedding -> GraphNorm -> dropout -> L x GLASSConv (GraphNorm / activation /
+    dropout between layers) -> optional JK concat -> final GraphNorm."""
+
+    def __init__(self, hidden_channels, output_channels, num_layers, max_deg, dropout=0, activation=nn.ReLU(),
+                 conv=GLASSConv, gn=True, jk=False, **kwargs):
+        super().__init__()
+        self.input_emb = nn.Embedding(max_deg + 1, hidden_channels, scale_grad_by_freq=False)
+        self.emb_gn = GraphNorm(hidden_channels)
+        self.convs = nn.ModuleList()
+        self.jk = jk
+        for _ in range(num_layers - 1):
+            self.convs.append(conv(in_channels=hidden_channels, out_channels=hidden_channels, activation=activation,
+                                   **kwargs))
+        self.convs.append(conv(in_channels=hidden_channels, out_channels=output_channels, activation=activation,
+                               **kwargs))
+        self.activation = activation
+        self.dropout = dropout
+        if gn:
+            self.gns = nn.ModuleList()
+            for _ in range(num_layers - 1):
+                self.gns.append(GraphNorm(hidden_channels))
+            if self.jk:
+                self.gns.append(GraphNorm(output_channels + (num_layers - 1) * hidden_channels))
+            else:
+                self.gns.append(GraphNorm(output_channels))
+        else:
+            self.gns = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.input_emb.reset_parameters()
+        self.emb_gn.reset_parameters()
+        for conv in self.convs:
+            conv.reset_parameters()
+        if self.gns is not None:
+            for gn in self.gns:
+                gn.reset_parameters()
+
+    def forward(self, x, edge_index, edge_weight, z=None):
+        if self.gns is None:
+            raise NotImplementedError("gn=False is outside the accelerated GLASS path (GLASSTest.py:150 uses gn=True)")
+        n = x.shape[0]
+        if z is None:  # every node takes the "labelled" branch, impl/models.py:242-244
+            mask = torch.ones(n, dtype=torch.uint8, device=x.device)
+        else:
+            mask = ops.label_mask(z)                                                        # :246
+        act = _act_id(self.activation)
+        h = ops.embedding(x.reshape(-1), self.input_emb.weight).reshape(n, -1)              # :248
+        h = self.emb_gn(h, p=self.dropout, training=self.training)                          # :249-251
+        xs = []
+        for layer, conv in enumerate(self.convs[:-1]):                                      # :253-259
+            h = conv(h, edge_index, edge_weight, mask)
+            xs.append(h)
+            h = self.gns[layer](h, act=act, p=self.dropout, training=self.training)
+        h = self.convs[-1](h, edge_index, edge_weight, mask)                                # :260
+        xs.append(h)
+        last = self.gns[-1]
+        if self.jk and len(xs) > 1:                                                         # :263-267
+            return ops.graph_norm_cat(xs, last.weight, last.bias, last.mean_scale, last.eps)
+        return last(xs[-1])                                                                 # :268-272
+
+
+# --- pooling --------------------------------------------------------------------------------------
+def global_add_pool(x, batch, size=None):
+    return ops.segment_pool_batch(x, batch, "sum", size)
+
+
+def global_mean_pool(x, batch, size=None):
+    return ops.segment_pool_batch(x, batch, "mean", size)
+
+
+def global_max_pool(x, batch, size=None):
+    return ops.segment_pool_batch(x, batch, "max", size)
+
+
+_POOL_MODE = {global_add_pool: "sum", global_mean_pool: "mean", global_max_pool: "max"}
+
+
+class PoolModule(nn.Module):
+    """impl/models.py:275-292.  ``forward(x, batch)`` pools rows that were already gathered;
+    ``pool_padded(emb, subG_node)`` is the fused path GLASS.Pool takes (no pad2batch, no gather)."""
+
+    def __init__(self, pool_fn, trans_fn=None):
+        super().__init__()
+        self.pool_fn = pool_fn
+        self.trans_fn = trans_fn
+
+    def padded_mode(self):
+        return _POOL_MODE.get(self.pool_fn) if self.trans_fn is None else None
+
+    def forward(self, x, batch):
+        if self.trans_fn is not None:
+            x = self.trans_fn(x)
+        return self.pool_fn(x, batch)
+
+    def pool_padded(self, emb, subG_node):
+        return ops.segment_pool(emb, subG_node, self.padded_mode())
+
+
+class AddPool(PoolModule):
+    def __init__(self, trans_fn=None):
+        super().__init__(global_add_pool, trans_fn)
+
+
+class MaxPool(PoolModule):
+    def __init__(self, trans_fn=None):
+        super().__init__(global_max_pool, trans_fn)
+
+
+class MeanPool(PoolModule):
+    def __init__(self, trans_fn=None):
+        super().__init__(global_mean_pool, trans_fn)
+
+
+class SizePool(AddPool):
+    """Sum of rows scaled by (segment size)^-1/2 (GraphSizeNorm then add, impl/models.py:310-319)."""
+
+    def __init__(self, trans_fn=None):
+        super().__init__(trans_fn)
+
+    def padded_mode(self):
+        return "size" if self.trans_fn is None else None
+
+    def forward(self, x, batch):
+        if x is not None and self.trans_fn is not None:
+            x = self.trans_fn(x)
+        return ops.segment_pool_batch(x, batch, "size")
+
+
+class GLASS(nn.Module):
+    """impl/models.py:322-355."""
+
+    def __init__(self, conv: EmbZGConv, preds: nn.ModuleList, pools: nn.ModuleList):
+        super().__init__()
+        self.conv = conv
+        self.preds = preds
+        self.pools = pools
+
+    def NodeEmb(self, x, edge_index, edge_weight, z=None):
+        embs = []
+        for c in range(x.shape[1]):                                                         # :338
+            embs.append(self.conv(x[:, c, :].reshape(x.shape[0], x.shape[-1]), edge_index, edge_weight, z))
+        if len(embs) == 1:  # mean over a single feature copy (always the case on this path) is the identity
+            return embs[0]
+        return torch.mean(torch.stack(embs, dim=1), dim=1)                                  # :342-343
+
+    def Pool(self, emb, subG_node, pool):
+        mode = pool.padded_mode() if isinstance(pool, PoolModule) else None
+        if mode is not None:
+            return ops.segment_pool(emb, subG_node, mode)                                   # fused :347-349
+        batch, pos = pad2batch(subG_node)                                                   # :347
+        return pool(ops.embedding(pos, emb), batch)                                         # :348-349
+
+    def forward(self, x, edge_index, edge_weight, subG_node, z=None, id=0):
+        emb = self.NodeEmb(x, edge_index, edge_weight, z)
+        emb = self.Pool(emb, subG_node, self.pools[id])
+        return self.preds[id](emb)

@@ -1,0 +1,633 @@
+"""torch custom ops over the C ABI of libglass_b200.so, plus their autograd formulas.
+
+Layering
+  * primitive ops ``torch.ops.glass_b200.*`` -- registered with torch.library for the CUDA dispatch
+    key only (a CPU tensor therefore fails loudly: there is no CPU path).  Each one is a thin ctypes
+    call into one ``extern "C"`` entry point of include/glass_b200.h on the current CUDA stream;
+    outputs and workspaces are torch tensors allocated by the caller (torch caching allocator), so
+    everything except csr_build is CUDA-graph capturable.
+  * autograd Functions (SpMM, PairLinearMix, GraphNorm, GraphNormCat, Embedding, SegmentPool) that
+    compose the primitives into the differentiable building blocks used by glass_b200.models.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_NONE, ACT_RELU, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
+
+__all__ = ["CSRAdj", "build_csr", "spmm", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
+           "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",
+           "set_gemm_path", "launch_count", "reset_launch_count"]
+
+# ---------------------------------------------------------------------------------------------
+# small helpers
+# ---------------------------------------------------------------------------------------------
+_launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+_gemm_path = {"auto": GEMM_AUTO, "simt": GEMM_SIMT, "tcgen05": GEMM_TCGEN05}[
+    os.environ.get("GLASS_B200_GEMM", "auto")]
+
+
+def set_gemm_path(name: str) -> None:
+    """'auto' | 'simt' | 'tcgen05' -- which kernel family evaluates the label-mixed Linear pairs."""
+    global _gemm_path
+    _gemm_path = {"auto": GEMM_AUTO, "simt": GEMM_SIMT, "tcgen05": GEMM_TCGEN05}[name]
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name: str, dim: Optional[int] = None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"glass_b200: `{name}` is on {t.device}; the hot path has no CPU implementation")
+    if t.dtype != dtype:
+        raise RuntimeError(f"glass_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise RuntimeError(f"glass_b200: `{name}` must be {dim}-d, got shape {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rowmajor(t: torch.Tensor):
+    """(tensor usable as a row-major matrix, leading dimension).  Column slices of a contiguous
+    matrix are accepted as-is (that is how the JK concat buffer is written without a copy)."""
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, t.shape[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# primitive ops (CUDA dispatch key only)
+# ---------------------------------------------------------------------------------------------
+_L = torch.library.Library("glass_b200", "DEF")
+
+
+def _define(schema: str, fn):
+    _L.define(schema)
+    _L.impl(schema.split("(")[0], fn, "CUDA")
+
+
+def _spmm_csr_(rowptr, col, val, x, y):
+    lib = _lib.load()
+    n_rows, h = y.shape
+    check(lib.glass_spmm_csr(_p(rowptr), _p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows, h,
+                             _stream()), "spmm_csr")
+    _count(1)
+
+
+_define("spmm_csr_(Tensor rowptr, Tensor col, Tensor val, Tensor x, Tensor(a!) y) -> ()", _spmm_csr_)
+
+
+def _pair_fwd_(a1, a2, w0, b0, w1, b1, mask, z_ratio, act, path, out, acts):
+    lib = _lib.load()
+    n, k1 = a1.shape
+    k2 = 0 if a2 is None else a2.shape[1]
+    h = w0.shape[0]
+    check(lib.glass_pair_linear_mix_fwd(_p(a1), a1.stride(0), k1, _p(a2), 0 if a2 is None else a2.stride(0), k2,
+                                        _p(w0), _p(b0), _p(w1), _p(b1), _p(mask), z_ratio, act, _p(out),
+                                        out.stride(0), _p(acts), n, h, path, _stream()), "pair_linear_mix_fwd")
+    _count(1)
+
+
+_define("pair_linear_mix_fwd_(Tensor a1, Tensor? a2, Tensor w0, Tensor b0, Tensor w1, Tensor b1, Tensor mask, "
+        "float z_ratio, int act, int path, Tensor(a!) out, Tensor(b!)? acts) -> ()", _pair_fwd_)
+
+
+def _pair_bwd_(dout, acts, a1, a2, w0, w1, mask, z_ratio, act, path, da1, da2, dw0, db0, dw1, db1, workspace):
+    lib = _lib.load()
+    n, k1 = a1.shape
+    k2 = 0 if a2 is None else a2.shape[1]
+    h = w0.shape[0]
+    check(lib.glass_pair_linear_mix_bwd(
+        _p(dout), dout.stride(0), _p(acts), _p(a1), a1.stride(0), k1, _p(a2), 0 if a2 is None else a2.stride(0), k2,
+        _p(w0), _p(w1), _p(mask), z_ratio, act, _p(da1), 0 if da1 is None else da1.stride(0), _p(da2),
+        0 if da2 is None else da2.stride(0), _p(dw0), _p(db0), _p(dw1), _p(db1), n, h, _p(workspace),
+        workspace.numel(), path, _stream()), "pair_linear_mix_bwd")
+    _count(3 if (da1 is not None or da2 is not None) else 2)
+
+
+_define("pair_linear_mix_bwd_(Tensor dout, Tensor? acts, Tensor a1, Tensor? a2, Tensor w0, Tensor w1, Tensor mask, "
+        "float z_ratio, int act, int path, Tensor(a!)? da1, Tensor(b!)? da2, Tensor(c!) dw0, Tensor(d!) db0, "
+        "Tensor(e!) dw1, Tensor(f!) db1, Tensor(g!) workspace) -> ()", _pair_bwd_)
+
+
+def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, pscale, out, stats, workspace):
+    lib = _lib.load()
+    n, c = x.shape
+    check(lib.glass_graphnorm_fwd(_p(x), x.stride(0), _p(weight), _p(bias), _p(mean_scale), eps, act, _p(keep),
+                                  pscale, _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
+                                  workspace.numel(), _stream()), "graphnorm_fwd")
+    _count(3)
+
+
+_define("graphnorm_fwd_(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, int act, Tensor? keep, "
+        "float pscale, Tensor(a!) out, Tensor(b!) stats, Tensor(c!) workspace) -> ()", _gn_fwd_)
+
+
+def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, pscale, dx, dweight, dbias, dmean_scale, workspace):
+    lib = _lib.load()
+    n, c = x.shape
+    check(lib.glass_graphnorm_bwd(_p(dout), dout.stride(0), _p(x), x.stride(0), _p(weight), _p(mean_scale),
+                                  _p(stats), act, _p(keep), pscale, _p(dx), dx.stride(0), _p(dweight), _p(dbias),
+                                  _p(dmean_scale), n, c, _p(workspace), workspace.numel(), _stream()),
+          "graphnorm_bwd")
+    _count(3)
+
+
+_define("graphnorm_bwd_(Tensor dout, Tensor x, Tensor weight, Tensor mean_scale, Tensor stats, int act, Tensor? keep, "
+        "float pscale, Tensor(a!) dx, Tensor(b!) dweight, Tensor(c!) dbias, Tensor(d!) dmean_scale, "
+        "Tensor(e!) workspace) -> ()", _gn_bwd_)
+
+
+def _emb_fwd_(table, ids, out):
+    lib = _lib.load()
+    check(lib.glass_embedding_fwd(_p(table), _p(ids), _p(out), out.stride(0), ids.numel(), table.shape[0],
+                                  table.shape[1], _stream()), "embedding_fwd")
+    _count(1)
+
+
+def _emb_bwd_(dout, ids, dtable):
+    lib = _lib.load()
+    check(lib.glass_embedding_bwd(_p(dout), dout.stride(0), _p(ids), _p(dtable), ids.numel(), dtable.shape[0],
+                                  dtable.shape[1], _stream()), "embedding_bwd")
+    _count(1)
+
+
+_define("embedding_fwd_(Tensor table, Tensor ids, Tensor(a!) out) -> ()", _emb_fwd_)
+_define("embedding_bwd_(Tensor dout, Tensor ids, Tensor(a!) dtable) -> ()", _emb_bwd_)
+
+
+def _pool_fwd_(emb, pos, mode, out, cnt, argmax):
+    lib = _lib.load()
+    b, lmax = pos.shape
+    check(lib.glass_segment_pool_fwd(_p(emb), emb.stride(0), _p(pos), b, lmax, mode, _p(out), out.stride(0), _p(cnt),
+                                     _p(argmax), emb.shape[1], emb.shape[0], _stream()), "segment_pool_fwd")
+    _count(1)
+
+
+def _pool_bwd_(dout, pos, mode, cnt, argmax, demb):
+    lib = _lib.load()
+    b, lmax = pos.shape
+    check(lib.glass_segment_pool_bwd(_p(dout), dout.stride(0), _p(pos), b, lmax, mode, _p(cnt), _p(argmax), _p(demb),
+                                     demb.stride(0), demb.shape[1], demb.shape[0], _stream()), "segment_pool_bwd")
+    _count(1)
+
+
+_define("segment_pool_fwd_(Tensor emb, Tensor pos, int mode, Tensor(a!) out, Tensor(b!) cnt, Tensor(c!)? argmax) -> ()",
+        _pool_fwd_)
+_define("segment_pool_bwd_(Tensor dout, Tensor pos, int mode, Tensor cnt, Tensor? argmax, Tensor(a!) demb) -> ()",
+        _pool_bwd_)
+
+
+def _pool_batch_fwd_(x, batch, n_seg, mode, out, cnt, argmax):
+    lib = _lib.load()
+    check(lib.glass_segment_pool_batch_fwd(_p(x), x.stride(0), _p(batch), x.shape[0], n_seg, mode, _p(out),
+                                           out.stride(0), _p(cnt), _p(argmax), x.shape[1], _stream()),
+          "segment_pool_batch_fwd")
+    _count(1)
+
+
+def _pool_batch_bwd_(dout, batch, n_seg, mode, cnt, argmax, dx):
+    lib = _lib.load()
+    check(lib.glass_segment_pool_batch_bwd(_p(dout), dout.stride(0), _p(batch), dx.shape[0], n_seg, mode, _p(cnt),
+                                           _p(argmax), _p(dx), dx.stride(0), dx.shape[1], _stream()),
+          "segment_pool_batch_bwd")
+    _count(1)
+
+
+_define("segment_pool_batch_fwd_(Tensor x, Tensor batch, int n_seg, int mode, Tensor(a!) out, Tensor(b!) cnt, "
+        "Tensor(c!)? argmax) -> ()", _pool_batch_fwd_)
+_define("segment_pool_batch_bwd_(Tensor dout, Tensor batch, int n_seg, int mode, Tensor cnt, Tensor? argmax, "
+        "Tensor(a!) dx) -> ()", _pool_batch_bwd_)
+
+
+def _maxzoz_(pos, z, mask):
+    lib = _lib.load()
+    check(lib.glass_maxzoz(_p(pos), pos.numel(), _p(z), _p(mask), z.numel(), _stream()), "maxzoz")
+    _count(1)
+
+
+def _label_mask_(z, mask):
+    lib = _lib.load()
+    check(lib.glass_label_mask(_p(z), _p(mask), z.numel(), _stream()), "label_mask")
+    _count(1)
+
+
+def _pad2batch_(pad, batch_out, pos_out, n_valid):
+    lib = _lib.load()
+    check(lib.glass_pad2batch(_p(pad), pad.shape[0], pad.shape[1], _p(batch_out), _p(pos_out), _p(n_valid),
+                              _stream()), "pad2batch")
+    _count(1)
+
+
+_define("maxzoz_(Tensor pos, Tensor(a!) z, Tensor(b!)? mask) -> ()", _maxzoz_)
+_define("label_mask_(Tensor z, Tensor(a!) mask) -> ()", _label_mask_)
+_define("pad2batch_(Tensor pad, Tensor(a!) batch_out, Tensor(b!) pos_out, Tensor(c!) n_valid) -> ()", _pad2batch_)
+
+_ops = torch.ops.glass_b200
+
+
+# ---------------------------------------------------------------------------------------------
+# buildAdj -> CSR
+# ---------------------------------------------------------------------------------------------
+class CSRAdj:
+    """Normalised adjacency as CSR plus the CSR of its transpose (what buildAdj returns here).
+
+    Stands in for the sparse COO tensor of impl/models.py:83-111: supports ``adj @ x``, ``.shape``
+    and, for inspection, ``indices()`` / ``values()`` in coalesced COO form."""
+
+    def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr):
+        self.n, self.aggr = n, aggr
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.rowptr_t, self.col_t, self.val_t = rowptr_t, col_t, val_t
+        self.deg = deg
+        self.shape = (n, n)
+
+    @property
+    def nnz(self) -> int:
+        return self.col.numel()
+
+    def indices(self) -> torch.Tensor:
+        counts = (self.rowptr[1:] - self.rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(self.n, device=self.col.device), counts)
+        return torch.stack((rows, self.col.long()))
+
+    def values(self) -> torch.Tensor:
+        return self.val
+
+    def coalesce(self):
+        return self
+
+    def t(self):
+        return CSRAdj(self.n, self.rowptr_t, self.col_t, self.val_t, self.rowptr, self.col, self.val, self.deg,
+                      self.aggr)
+
+    def __matmul__(self, x):
+        return spmm(self, x)
+
+
+def build_csr(edge_index: torch.Tensor, edge_weight: torch.Tensor, n_node: int, aggr: str) -> CSRAdj:
+    """GPU restatement of buildAdj (impl/models.py:83-111); raises NotImplementedError for an unknown aggr."""
+    if aggr not in AGGR:
+        raise NotImplementedError(aggr)  # impl/models.py:110-111
+    lib = _lib.load()
+    ei = _req(edge_index, torch.int64, "edge_index", 2)
+    ew = _req(edge_weight, torch.float32, "edge_weight", 1)
+    nnz = ei.shape[1]
+    dev = ei.device
+    with torch.cuda.device(dev):
+        ws_bytes = lib.glass_csr_build_workspace_bytes(nnz, n_node)
+        if ws_bytes == 0:
+            check(-1, "csr_build_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        rowptr, rowptr_t = torch.empty(n_node + 1, **i32), torch.empty(n_node + 1, **i32)
+        col, col_t = torch.empty(nnz, **i32), torch.empty(nnz, **i32)
+        val, val_t = torch.empty(nnz, **f32), torch.empty(nnz, **f32)
+        deg = torch.empty(n_node, **f32)
+        nnz_out = C.c_int64(0)
+        check(lib.glass_csr_build(_p(ei), _p(ew), nnz, n_node, AGGR[aggr], _p(rowptr), _p(col), _p(val),
+                                  _p(rowptr_t), _p(col_t), _p(val_t), _p(deg), C.byref(nnz_out), _p(ws), ws_bytes,
+                                  _stream()), "csr_build")
+        _count(8)
+    m = nnz_out.value
+    if m != nnz:  # duplicates were merged
+        col, val, col_t, val_t = col[:m].clone(), val[:m].clone(), col_t[:m].clone(), val_t[:m].clone()
+    return CSRAdj(n_node, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr)
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd building blocks
+# ---------------------------------------------------------------------------------------------
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, adj: CSRAdj):
+        x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
+        y = torch.empty((adj.n, x.shape[1]), dtype=torch.float32, device=x.device)
+        _ops.spmm_csr_(adj.rowptr, adj.col, adj.val, x, y)
+        ctx.adj = adj
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        adj = ctx.adj
+        gy, _ = _rowmajor(gy)
+        gx = torch.empty_like(gy, memory_format=torch.contiguous_format)
+        _ops.spmm_csr_(adj.rowptr_t, adj.col_t, adj.val_t, gy, gx)  # dX = A^T dY
+        return gx, None
+
+
+def spmm(adj: CSRAdj, x: torch.Tensor) -> torch.Tensor:
+    """``adj @ x`` (impl/models.py:164)."""
+    return _SpMM.apply(x, adj)
+
+
+class _PairLinearMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a1, a2, w0, b0, w1, b1, mask, z_ratio, act, path):
+        a1, _ = _rowmajor(_req(a1, torch.float32, "a1", 2))
+        if a2 is not None:
+            a2, _ = _rowmajor(_req(a2, torch.float32, "a2", 2))
+        w0, b0 = _req(w0, torch.float32, "w0", 2), _req(b0, torch.float32, "b0", 1)
+        w1, b1 = _req(w1, torch.float32, "w1", 2), _req(b1, torch.float32, "b1", 1)
+        mask = _req(mask, torch.uint8, "mask", 1)
+        n, h = a1.shape[0], w0.shape[0]
+        k = a1.shape[1] + (0 if a2 is None else a2.shape[1])
+        if w0.shape != (h, k) or w1.shape != (h, k) or mask.shape[0] != n:
+            raise RuntimeError(f"pair_linear_mix: shape mismatch a={n}x{k} w0={tuple(w0.shape)} w1={tuple(w1.shape)}")
+        need_grad = any(ctx.needs_input_grad[:6])
+        out = torch.empty((n, h), dtype=torch.float32, device=a1.device)
+        acts = (torch.empty((n, 2 * h), dtype=torch.float32, device=a1.device)
+                if (need_grad and act != ACT_NONE) else None)
+        _ops.pair_linear_mix_fwd_(a1, a2, w0, b0, w1, b1, mask, float(z_ratio), act, path, out, acts)
+        ctx.save_for_backward(a1, a2, w0, w1, mask, acts)
+        ctx.cfg = (float(z_ratio), act, path)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a1, a2, w0, w1, mask, acts = ctx.saved_tensors
+        z_ratio, act, path = ctx.cfg
+        dout, _ = _rowmajor(dout)
+        n, h = dout.shape
+        k = w0.shape[1]
+        dev = dout.device
+        da1 = torch.empty_like(a1, memory_format=torch.contiguous_format) if ctx.needs_input_grad[0] else None
+        da2 = (torch.empty_like(a2, memory_format=torch.contiguous_format)
+               if (a2 is not None and ctx.needs_input_grad[1]) else None)
+        dw0, dw1 = torch.empty_like(w0), torch.empty_like(w1)
+        db0 = torch.empty(h, dtype=torch.float32, device=dev)
+        db1 = torch.empty(h, dtype=torch.float32, device=dev)
+        ws = torch.empty(_lib.load().glass_pair_linear_mix_bwd_workspace_bytes(n, h, k), dtype=torch.uint8, device=dev)
+        _ops.pair_linear_mix_bwd_(dout, acts, a1, a2, w0, w1, mask, z_ratio, act, path, da1, da2, dw0, db0, dw1, db1,
+                                  ws)
+        return da1, da2, dw0, db0, dw1, db1, None, None, None, None
+
+
+def pair_linear_mix(a1, a2, w0, b0, w1, b1, mask, z_ratio: float, act: int, path: Optional[int] = None):
+    """where(mask, z*p1+(1-z)*p0, z*p0+(1-z)*p1) with p_i = act([a1|a2] W_i^T + b_i)
+    (impl/models.py:158-162 and :167-173)."""
+    return _PairLinearMix.apply(a1, a2, w0, b0, w1, b1, mask, z_ratio, act, _gemm_path if path is None else path)
+
+
+_keep_queue: Optional[List[torch.Tensor]] = None
+
+
+@contextlib.contextmanager
+def inject_keep_masks(masks: Sequence[torch.Tensor]):
+    """Testing hook: dropout keep-masks (uint8 [n, c]) consumed in call order instead of fresh draws,
+    so a train()-mode pass can be compared element-wise with the oracle given the same masks."""
+    global _keep_queue
+    _keep_queue = list(masks)
+    try:
+        yield
+    finally:
+        _keep_queue = None
+
+
+def _draw_keep(n, c, p, device):
+    if _keep_queue is not None:
+        m = _keep_queue.pop(0)
+        assert m.shape == (n, c), (m.shape, (n, c))
+        return _req(m, torch.uint8, "keep", 2)
+    return torch.empty((n, c), dtype=torch.uint8, device=device).bernoulli_(1.0 - p)
+
+
+def _gn_workspace(n, c, device):
+    return torch.empty(_lib.load().glass_graphnorm_workspace_bytes(n, c), dtype=torch.uint8, device=device)
+
+
+class _GraphNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mean_scale, eps, act, p, training):
+        x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
+        weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
+        mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
+        n, c = x.shape
+        keep, pscale = None, 1.0
+        if training and p > 0.0:
+            if p >= 1.0:
+                raise RuntimeError("dropout p must be < 1")
+            keep, pscale = _draw_keep(n, c, p, x.device), 1.0 / (1.0 - p)
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        stats = torch.empty((5, c), dtype=torch.float32, device=x.device)
+        _ops.graphnorm_fwd_(x, weight, bias, mean_scale, float(eps), act, keep, pscale, out, stats,
+                            _gn_workspace(n, c, x.device))
+        ctx.save_for_backward(x, weight, mean_scale, stats, keep)
+        ctx.cfg = (act, pscale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, mean_scale, stats, keep = ctx.saved_tensors
+        act, pscale = ctx.cfg
+        dout, _ = _rowmajor(dout)
+        n, c = x.shape
+        dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
+        _ops.graphnorm_bwd_(dout, x, weight, mean_scale, stats, act, keep, pscale, dx, dw, db, da,
+                            _gn_workspace(n, c, x.device))
+        return dx, dw, db, da, None, None, None, None
+
+
+def graph_norm(x, weight, bias, mean_scale, eps: float = 1e-5, act: int = ACT_NONE, p: float = 0.0,
+               training: bool = False):
+    """dropout(act(GraphNorm(x))) over the whole graph (PyG GraphNorm, batch=None; impl/models.py:165-166,
+    249-251, 257-259).  act / dropout are the ops the reference applies right after the norm."""
+    return _GraphNorm.apply(x, weight, bias, mean_scale, eps, act, p, training)
+
+
+class _GraphNormCat(torch.autograd.Function):
+    """gns[-1](torch.cat(xs, -1)) of impl/models.py:263-267: GraphNorm is per column, so every xs[l] is
+    normalised with its slice of the parameters straight into its column block of the output."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, mean_scale, eps, *xs):
+        xs = [_rowmajor(_req(t, torch.float32, "xs", 2))[0] for t in xs]
+        n = xs[0].shape[0]
+        widths = [t.shape[1] for t in xs]
+        d = sum(widths)
+        weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
+        mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
+        if weight.numel() != d:
+            raise RuntimeError(f"graph_norm_cat: {d} columns but {weight.numel()} parameters")
+        out = torch.empty((n, d), dtype=torch.float32, device=xs[0].device)
+        stats, off = [], 0
+        for t, w in zip(xs, widths):
+            st = torch.empty((5, w), dtype=torch.float32, device=t.device)
+            _ops.graphnorm_fwd_(t, weight[off:off + w], bias[off:off + w], mean_scale[off:off + w], float(eps),
+                                ACT_NONE, None, 1.0, out[:, off:off + w], st, _gn_workspace(n, w, t.device))
+            stats.append(st)
+            off += w
+        ctx.save_for_backward(weight, mean_scale, *xs, *stats)
+        ctx.widths = widths
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        widths = ctx.widths
+        L = len(widths)
+        weight, mean_scale = ctx.saved_tensors[:2]
+        xs, stats = ctx.saved_tensors[2:2 + L], ctx.saved_tensors[2 + L:]
+        dout, _ = _rowmajor(dout)
+        n = dout.shape[0]
+        dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
+        dxs, off = [], 0
+        for t, st, w in zip(xs, stats, widths):
+            dx = torch.empty((n, w), dtype=torch.float32, device=t.device)
+            _ops.graphnorm_bwd_(dout[:, off:off + w], t, weight[off:off + w], mean_scale[off:off + w], st, ACT_NONE,
+                                None, 1.0, dx, dw[off:off + w], db[off:off + w], da[off:off + w],
+                                _gn_workspace(n, w, t.device))
+            dxs.append(dx)
+            off += w
+        return (dw, db, da, None, *dxs)
+
+
+def graph_norm_cat(xs: Sequence[torch.Tensor], weight, bias, mean_scale, eps: float = 1e-5):
+    return _GraphNormCat.apply(weight, bias, mean_scale, eps, *xs)
+
+
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table):
+        ids = _req(ids, torch.int64, "ids").reshape(-1)
+        table = _req(table, torch.float32, "table", 2)
+        out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+        _ops.embedding_fwd_(table, ids, out)
+        ctx.save_for_backward(ids)
+        ctx.rows = table.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        dout, _ = _rowmajor(dout)
+        dtable = torch.zeros((ctx.rows, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        _ops.embedding_bwd_(dout, ids, dtable)
+        return None, dtable
+
+
+def embedding(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """table[ids] (nn.Embedding lookup of impl/models.py:248; also the emb[pos] gather of :348)."""
+    return _Embedding.apply(ids, table)
+
+
+class _SegmentPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, pos, mode):
+        emb, _ = _rowmajor(_req(emb, torch.float32, "emb", 2))
+        pos = _req(pos, torch.int64, "subG_node", 2)
+        b, d = pos.shape[0], emb.shape[1]
+        out = torch.empty((b, d), dtype=torch.float32, device=emb.device)
+        cnt = torch.empty(b, dtype=torch.float32, device=emb.device)
+        argmax = torch.empty((b, d), dtype=torch.int32, device=emb.device) if mode == POOL["max"] else None
+        _ops.segment_pool_fwd_(emb, pos, mode, out, cnt, argmax)
+        ctx.save_for_backward(pos, cnt, argmax)
+        ctx.cfg = (mode, emb.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pos, cnt, argmax = ctx.saved_tensors
+        mode, n = ctx.cfg
+        dout, _ = _rowmajor(dout)
+        demb = torch.zeros((n, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        _ops.segment_pool_bwd_(dout, pos, mode, cnt, argmax, demb)
+        return demb, None, None
+
+
+def segment_pool(emb: torch.Tensor, subG_node: torch.Tensor, mode: str) -> torch.Tensor:
+    """GLASS.Pool (impl/models.py:346-350) fused: pad2batch + emb[pos] + {Add,Mean,Max,Size}Pool."""
+    if mode not in POOL:
+        raise NotImplementedError(mode)  # GLASSTest.py:171
+    return _SegmentPool.apply(emb, subG_node, POOL[mode])
+
+
+class _SegmentPoolBatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, batch, n_seg, mode):
+        x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
+        batch = _req(batch, torch.int64, "batch", 1)
+        d = x.shape[1]
+        out = torch.empty((n_seg, d), dtype=torch.float32, device=x.device)
+        cnt = torch.empty(n_seg, dtype=torch.float32, device=x.device)
+        argmax = torch.empty((n_seg, d), dtype=torch.int32, device=x.device) if mode == POOL["max"] else None
+        _ops.segment_pool_batch_fwd_(x, batch, n_seg, mode, out, cnt, argmax)
+        ctx.save_for_backward(batch, cnt, argmax)
+        ctx.cfg = (mode, n_seg, x.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        batch, cnt, argmax = ctx.saved_tensors
+        mode, n_seg, m = ctx.cfg
+        dout, _ = _rowmajor(dout)
+        dx = torch.empty((m, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        _ops.segment_pool_batch_bwd_(dout, batch, n_seg, mode, cnt, argmax, dx)
+        return dx, None, None, None
+
+
+def segment_pool_batch(x: torch.Tensor, batch: torch.Tensor, mode: str, size: Optional[int] = None):
+    """PoolModule.forward(x, batch) (impl/models.py:287-292) for rows already gathered; batch sorted ascending.
+    Like PyG, the number of segments is batch.max()+1 unless `size` is given (one host sync)."""
+    if mode not in POOL:
+        raise NotImplementedError(mode)
+    n_seg = int(batch.max().item()) + 1 if size is None else int(size)
+    return _SegmentPoolBatch.apply(x, batch, n_seg, POOL[mode])
+
+
+# ---------------------------------------------------------------------------------------------
+# labels / index helpers (no gradients)
+# ---------------------------------------------------------------------------------------------
+def maxzoz(n_node: int, pos: torch.Tensor, with_mask: bool = False):
+    """Max-zero-one labels (impl/utils.py:32-45): int64 z[N]; optionally also the uint8 mask z > 0."""
+    pos = _req(pos, torch.int64, "pos")
+    z = torch.empty(n_node, dtype=torch.int64, device=pos.device)
+    mask = torch.empty(n_node, dtype=torch.uint8, device=pos.device) if with_mask else None
+    _ops.maxzoz_(pos, z, mask)
+    return (z, mask) if with_mask else z
+
+
+def label_mask(z: torch.Tensor) -> torch.Tensor:
+    """uint8 (z > 0.5) of impl/models.py:246."""
+    z = _req(z, torch.int64, "z").reshape(-1)
+    mask = torch.empty(z.numel(), dtype=torch.uint8, device=z.device)
+    _ops.label_mask_(z, mask)
+    return mask
+
+
+def pad2batch(pad: torch.Tensor):
+    """impl/utils.py:18-29 on the GPU (one host sync for the output length, as in the reference)."""
+    pad = _req(pad, torch.int64, "pad", 2)
+    total = pad.numel()
+    batch = torch.empty(total, dtype=torch.int64, device=pad.device)
+    pos = torch.empty(total, dtype=torch.int64, device=pad.device)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=pad.device)
+    _ops.pad2batch_(pad, batch, pos, n_valid)
+    m = int(n_valid.item())
+    return batch[:m], pos[:m]

@@ -1,0 +1,175 @@
+/*
+ * glass_b200.h -- C ABI of libglass_b200.so: hand-written sm_100a kernels for the GLASS
+ * labeled message-passing hot path (reference: Xi-yuanWang/GLASS, impl/models.py, impl/utils.py).
+ *
+ * The reference is pure Python on PyTorch/PyG and has no FFI of its own; every entry point below
+ * replaces a group of ATen / PyG library calls at the cited reference lines.  The Python host
+ * layer (glass_b200/ops.py) binds these with ctypes and registers them as torch custom ops;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  No allocation, no free,
+ *     no host synchronisation inside any entry point except glass_csr_build (init path, which
+ *     returns the de-duplicated entry count to the host).  Everything else is CUDA-graph capturable.
+ *   - Dense matrices are row-major fp32 with an explicit leading dimension `ld*` in elements.
+ *   - Index arrays handed in by the reference API are int64 (torch default); the CSR produced and
+ *     consumed here uses int32 (n_node, nnz < 2^31).
+ *   - `stream` is a cudaStream_t passed as void*; NULL is the legacy default stream.
+ *   - Return value: 0 on success, a negative glass_status otherwise; glass_last_error() gives
+ *     the message of the last failure on the calling thread.  No entry point ever falls back
+ *     to a CPU path.
+ */
+#ifndef GLASS_B200_H_
+#define GLASS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLASS_B200_ABI_VERSION 1
+
+typedef enum {
+    GLASS_OK = 0,
+    GLASS_ERR_BAD_ARG = -1,      /* shape / enum / alignment not supported */
+    GLASS_ERR_CUDA = -2,         /* a CUDA runtime call or launch failed */
+    GLASS_ERR_WORKSPACE = -3,    /* workspace too small */
+    GLASS_ERR_UNSUPPORTED = -4   /* configuration outside the kernel's envelope */
+} glass_status;
+
+typedef enum { GLASS_AGGR_MEAN = 0, GLASS_AGGR_SUM = 1, GLASS_AGGR_GCN = 2 } glass_aggr;       /* impl/models.py:95-109 */
+typedef enum { GLASS_ACT_NONE = 0, GLASS_ACT_RELU = 1, GLASS_ACT_ELU = 2 } glass_act;          /* GLASSTest.py:143 passes ELU */
+typedef enum { GLASS_POOL_SUM = 0, GLASS_POOL_MEAN = 1, GLASS_POOL_MAX = 2, GLASS_POOL_SIZE = 3 } glass_pool; /* impl/models.py:295-319 */
+typedef enum { GLASS_GEMM_AUTO = 0, GLASS_GEMM_SIMT = 1, GLASS_GEMM_TCGEN05 = 2 } glass_gemm_path;
+
+int glass_abi_version(void);
+const char* glass_last_error(void);
+/* Number of SMs of the current device (grid sizing); negative glass_status on failure. */
+int glass_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * buildAdj  (impl/models.py:83-111) -> CSR + transposed CSR
+ *
+ * Input: COO edge_index int64 [2, nnz] (row = edge_index[0..nnz), col = edge_index[nnz..2nnz)),
+ * edge_weight fp32 [nnz].  Any order, duplicates and self loops allowed.  Semantics
+ * (bit-exact vs. buildAdj(...).coalesce() for unit weights, see oracle/glass_oracle.py
+ * build_csr_numpy): deg = row sums of the raw entries; deg < 0.5 -> += 1; mean: (1/deg)[r]*w;
+ * sum: w; gcn: ((deg^-1/2)[r]*w)*(deg^-1/2)[c] with IEEE 1/sqrt; duplicates normalised first, then
+ * summed in input order; entries sorted by (row, col).
+ * Outputs (capacity nnz each): rowptr/rowptr_t int32 [n_node+1], col/col_t int32, val/val_t fp32,
+ * deg fp32 [n_node] (after the +1 fix).  *nnz_out_host receives the number of distinct entries.
+ * The transposed triple is the CSR of A^T (needed by backward: `mean` is not symmetric).
+ * ------------------------------------------------------------------------------------------ */
+size_t glass_csr_build_workspace_bytes(int64_t nnz, int64_t n_node);
+int glass_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t nnz, int64_t n_node,
+                    int aggr, int32_t* rowptr, int32_t* col, float* val, int32_t* rowptr_t,
+                    int32_t* col_t, float* val_t, float* deg, int64_t* nnz_out_host, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * adj @ x  (impl/models.py:164; backward = the same kernel on the transposed CSR)
+ * y[r, :] = sum_{e in row r} val[e] * x[col[e], :]  accumulated in CSR order (deterministic).
+ * n_rows = rows of the CSR block; x must hold every column index referenced.
+ * ------------------------------------------------------------------------------------------ */
+int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
+                   int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int h, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Label-mixed pair of Linear layers  (impl/models.py:158-162 with activation, :169-173 without)
+ *   p0 = act([a1|a2] W0^T + b0), p1 = act([a1|a2] W1^T + b1)
+ *   out = mask ? z*p1 + (1-z)*p0 : z*p0 + (1-z)*p1
+ * a1 [n,k1], a2 [n,k2] (a2 may be NULL with k2 = 0: the virtual concat of models.py:167),
+ * w0,w1 [h, k1+k2] row-major (nn.Linear layout), b0,b1 [h], mask uint8 [n] (1 = labelled node).
+ * acts [n, 2h] (ld 2h) receives the post-activation p0|p1 when non-NULL (saved for backward;
+ * pass NULL for act == NONE or inference).  path selects SIMT fp32 or tcgen05 (3xTF32).
+ * ------------------------------------------------------------------------------------------ */
+int glass_pair_linear_mix_fwd(const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2, int k2,
+                              const float* w0, const float* b0, const float* w1, const float* b1,
+                              const uint8_t* mask, float z_ratio, int act, float* out, int64_t ldo,
+                              float* acts, int64_t n, int h, int path, void* stream);
+
+/* Backward of the above.  dout [n,h]; acts as saved by fwd (NULL iff act == NONE).
+ * da1 [n,k1], da2 [n,k2] (either may be NULL to skip), dw0,dw1 [h,k1+k2], db0,db1 [h].
+ * workspace: glass_pair_linear_mix_bwd_workspace_bytes(n, h, k1+k2) bytes (split-N partials,
+ * reduced in a fixed order => deterministic). */
+size_t glass_pair_linear_mix_bwd_workspace_bytes(int64_t n, int h, int k);
+int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts, const float* a1,
+                              int64_t lda1, int k1, const float* a2, int64_t lda2, int k2,
+                              const float* w0, const float* w1, const uint8_t* mask, float z_ratio, int act,
+                              float* da1, int64_t ldda1, float* da2, int64_t ldda2, float* dw0, float* db0,
+                              float* dw1, float* db1, int64_t n, int h, void* workspace,
+                              size_t workspace_bytes, int path, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GraphNorm over the whole graph (PyG GraphNorm with batch=None; call sites impl/models.py:165,
+ * 249, 257, 266), optionally followed by the activation and dropout that the reference applies
+ * right after it (impl/models.py:166, 251, 258-259).
+ *   mu = mean_rows(x); o = x - mean_scale*mu; var = mean_rows(o^2); rstd = 1/sqrt(var+eps)
+ *   out = keep * pscale * act(weight*o*rstd + bias)
+ * stats [5, c]: rows = scale (weight*rstd), am (mean_scale*mu), mu, rstd, bias -- written by fwd,
+ * consumed by bwd.  keep: uint8 [n,c] (ld c) or NULL; pscale = 1/(1-p).
+ * Column sums are accumulated in fp64 per block and reduced in block order (deterministic).
+ * workspace: glass_graphnorm_workspace_bytes(n, c).
+ * ------------------------------------------------------------------------------------------ */
+size_t glass_graphnorm_workspace_bytes(int64_t n, int c);
+int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
+                        const float* mean_scale, float eps, int act, const uint8_t* keep, float pscale,
+                        float* out, int64_t ldo, float* stats, int64_t n, int c, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* dx [n,c]; dweight, dbias, dmean_scale [c] are OVERWRITTEN (not accumulated). */
+int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* weight,
+                        const float* mean_scale, const float* stats, int act, const uint8_t* keep,
+                        float pscale, float* dx, int64_t lddx, float* dweight, float* dbias,
+                        float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * nn.Embedding lookup (impl/models.py:248) and its dense gradient.
+ * ids int64 [n]; table [rows, h]; out [n, h].  bwd ACCUMULATES into dtable (caller zero-fills).
+ * ------------------------------------------------------------------------------------------ */
+int glass_embedding_fwd(const float* table, const int64_t* ids, float* out, int64_t ldo, int64_t n,
+                        int64_t rows, int h, void* stream);
+int glass_embedding_bwd(const float* dout, int64_t lddo, const int64_t* ids, float* dtable, int64_t n,
+                        int64_t rows, int h, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Padded-subgraph pooling (GLASS.Pool impl/models.py:346-350 = pad2batch + emb[pos] + pool_fn;
+ * pools impl/models.py:295-319).  pos int64 [b, lmax], -1 = padding.  One CTA per subgraph reads
+ * the padded row directly; rows are accumulated in pad order (same order as the reference's
+ * index_add).  out [b, d]; cnt fp32 [b] (valid nodes per row); argmax int32 [b, d] (MAX only,
+ * else may be NULL): node id of the first maximum, -1 for an empty row.
+ * bwd ACCUMULATES into demb [n_node, d] (caller zero-fills) with atomics.
+ * ------------------------------------------------------------------------------------------ */
+int glass_segment_pool_fwd(const float* emb, int64_t lde, const int64_t* pos, int64_t b, int64_t lmax,
+                           int mode, float* out, int64_t ldo, float* cnt, int32_t* argmax, int d,
+                           int64_t n_node, void* stream);
+int glass_segment_pool_bwd(const float* dout, int64_t lddo, const int64_t* pos, int64_t b, int64_t lmax,
+                           int mode, const float* cnt, const int32_t* argmax, float* demb, int64_t ldde,
+                           int d, int64_t n_node, void* stream);
+/* PoolModule.forward(x, batch) (impl/models.py:287-292): x [m, d] rows already gathered,
+ * batch int64 [m] sorted ascending (as pad2batch produces). */
+int glass_segment_pool_batch_fwd(const float* x, int64_t ldx, const int64_t* batch, int64_t m, int64_t n_seg,
+                                 int mode, float* out, int64_t ldo, float* cnt, int32_t* argmax, int d,
+                                 void* stream);
+int glass_segment_pool_batch_bwd(const float* dout, int64_t lddo, const int64_t* batch, int64_t m,
+                                 int64_t n_seg, int mode, const float* cnt, const int32_t* argmax, float* dx,
+                                 int64_t lddx, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Max-zero-one labels (impl/utils.py:32-45) and the bool mask of impl/models.py:246.
+ * z int64 [n_node] is fully overwritten: 1 where the node occurs in pos, else 0.
+ * mask uint8 [n_node] = (z > 0)  ( == z > 0.5 for integer z).
+ * pad2batch (impl/utils.py:18-29): batch_out/pos_out capacity b*lmax; *n_valid (device int64).
+ * ------------------------------------------------------------------------------------------ */
+int glass_maxzoz(const int64_t* pos, int64_t n_pos, int64_t* z, uint8_t* mask_or_null, int64_t n_node,
+                 void* stream);
+int glass_label_mask(const int64_t* z, uint8_t* mask, int64_t n_node, void* stream);
+int glass_pad2batch(const int64_t* pad, int64_t b, int64_t lmax, int64_t* batch_out, int64_t* pos_out,
+                    int64_t* n_valid, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLASS_B200_H_ */
