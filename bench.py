@@ -211,7 +211,7 @@ def run_product(args):
     from glass_b200 import build as _build
     _build.build()
     from glass_b200 import ops, run, train, utils
-    from glass_b200.dist import FlatGradAllReduce
+    from glass_b200.graphed import GraphedTrainStep, train_epoch
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -225,20 +225,18 @@ def run_product(args):
                             wl["max_deg"], wl["out_dim"], pretrained=wl["table"], device=dev)
     x, ei, ew = g.x.to(dev), g.edge_index.to(dev), g.edge_attr.to(dev)
     loss_fn = wl["loss_fn"]
-    opt = torch.optim.Adam(model.parameters(), lr=p["lr"])
-    flat = FlatGradAllReduce(model.parameters())
     n_total = args.warmup + args.steps
     host_batches = [(pos.pin_memory(), y.pin_memory()) for pos, y in batches_for(wl, n_total, rank, world)]
     dev_batches = [(pos.to(dev), y.to(dev)) for pos, y in host_batches]
-
-    def step(pos, y):
-        z = utils.MaxZOZ(x, pos)
-        flat.zero()
-        loss = loss_fn(model(x, ei, ew, pos, z, id=0), y)
-        loss.backward()
-        flat.allreduce_mean()
-        opt.step()
-        return loss
+    # one captured CUDA graph per step: labels, forward, loss, backward, (NCCL all-reduce), Adam
+    ops.reset_launch_count()
+    step = GraphedTrainStep(model, loss_fn, x, ei, ew, dev_batches[0][0], dev_batches[0][1], p["lr"], warmup=3)
+    ops.reset_launch_count()
+    if not args.no_graph:
+        step.capture()
+    else:
+        step(*dev_batches[0])
+    launches_per_step = ops.launch_count()
 
     def barrier():
         if world > 1:
@@ -250,7 +248,6 @@ def run_product(args):
     for pos, y in dev_batches[:args.warmup]:
         step(pos, y)
     barrier()
-    ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
@@ -259,7 +256,7 @@ def run_product(args):
             step(pos, y)
         e1.record()
         barrier()
-    launches = ops.launch_count()
+    launches = launches_per_step * args.steps
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -268,26 +265,9 @@ def run_product(args):
     value = bs * args.steps * world / (ms * 1e-3)
 
     # ---- e2e: public train API, host buffers -> device every step, loss read back every step
-    class HostLoader:
-        def __iter__(self):
-            for pos, y in host_batches[args.warmup:]:
-                pd, yd = pos.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
-                yield x, ei, ew, pd, utils.MaxZOZ(x, pd), yd
-
-        def __len__(self):
-            return args.steps
-
-    class Opt:  # train.train calls optimizer.zero_grad()/step(); route them to the flat buffer + allreduce
-        def zero_grad(self):
-            flat.zero()
-
-        def step(self):
-            flat.allreduce_mean()
-            opt.step()
-
     barrier()
     t0 = time.perf_counter()
-    train.train(Opt(), model, HostLoader(), loss_fn)
+    train_epoch(step, host_batches[args.warmup:], sync_each_step=True)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -298,7 +278,8 @@ def run_product(args):
     if rank == 0:
         line = base_line(args, wl, value, ms / args.steps)
         line["e2e"] = {"value": e2e_value, "unit": "subgraphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                       "api": "glass_b200.train.train"}
+                       "api": "glass_b200.graphed.train_epoch(GraphedTrainStep, pinned host batches), loss.item() every step"}
+        line["config"]["cuda_graph"] = not args.no_graph
         line["gpu_launches"] = launches
         line["clocks"] = clocks.summary()
         adj = model.conv.convs[0].adj
@@ -338,6 +319,7 @@ def main():
     ap.add_argument("--workload", default="em_user_shaped")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

@@ -1,0 +1,99 @@
+"""Whole-step CUDA graph: labels -> forward -> loss -> backward -> (all-reduce) -> Adam, one replay per step.
+
+The reference's loop (impl/train.py:8-16) issues ~10^2 small launches and one host sync per step; on
+every shipped config the GPU work per step is shorter than the Python time needed to launch it
+(SURVEY.md section 7 "hard parts" 1).  All kernels of libglass_b200.so are capture-safe (no allocation,
+no host sync), shapes are static per dataset (fixed batch size with drop_last, globally padded
+subG_node), so the step is captured once and replayed with new (subG_node, y) copied into static
+buffers.  Semantics are those of impl/train.py:10-16 with Adam (GLASSTest.py:213).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import utils
+from .dist import FlatGradAllReduce
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn: Callable, x, edge_index, edge_weight, pos_example: torch.Tensor,
+                 y_example: torch.Tensor, lr: float, group=None, warmup: int = 3, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay: float = 0.0, z_fn=utils.MaxZOZ):
+        dev = x.device
+        self.model, self.loss_fn, self.z_fn = model, loss_fn, z_fn
+        self.x, self.ei, self.ew = x, edge_index, edge_weight
+        self.pos = torch.empty_like(pos_example, device=dev)
+        self.y = torch.empty_like(y_example, device=dev)
+        self.pos.copy_(pos_example)
+        self.y.copy_(y_example)
+        self.flat = FlatGradAllReduce(model.parameters(), group)
+        self.lr = torch.tensor(float(lr), device=dev)
+        self.opt = torch.optim.Adam(model.parameters(), lr=self.lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                    capturable=True, foreach=True)
+        self.loss = torch.zeros((), device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        model.train()
+        # warm-up on a side stream (builds the CSR cache, initialises Adam state, primes the allocator)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+
+    # one iteration of impl/train.py:10-16
+    def _step_eager(self):
+        z = self.z_fn(self.x, self.pos)
+        self.flat.zero()
+        loss = self.loss_fn(self.model(self.x, self.ei, self.ew, self.pos, z, id=0), self.y)
+        loss.backward()
+        self.flat.allreduce_mean()
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def capture(self):
+        """Capture after restoring nothing: the warm-up steps DID update the parameters; callers that need
+        an untouched model should snapshot/restore the state_dict around construction (see reset_to)."""
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_eager()
+        self.flat.check_views()
+        return self
+
+    def reset_to(self, state_dict):
+        """Restore parameters and clear Adam moments / step counters (in place: graph addresses stay valid)."""
+        with torch.no_grad():
+            own = self.model.state_dict()
+            for k, v in state_dict.items():
+                own[k].copy_(v)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def set_lr(self, lr: float):
+        self.lr.fill_(float(lr))
+
+    def __call__(self, pos: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """pos/y may live on the host (pinned) or the device; returns the (device) loss of this step."""
+        self.pos.copy_(pos, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.graph is None:
+            self._step_eager()
+        else:
+            self.graph.replay()
+        return self.loss
+
+
+def train_epoch(step: GraphedTrainStep, batches, sync_each_step: bool = True) -> float:
+    """impl/train.py:4-17 over an iterable of (subG_node, y) batches using the captured step."""
+    losses = []
+    for pos, y in batches:
+        loss = step(pos, y)
+        losses.append(loss.item() if sync_each_step else loss.clone())
+    if sync_each_step:
+        return sum(losses) / len(losses)
+    return float(torch.stack(losses).double().sum().item()) / len(losses)

@@ -1,0 +1,56 @@
+"""CPU, world_size 2, gloo: host-side logic of label-batch data parallelism (no kernels involved)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from glass_b200.dist import FlatGradAllReduce, shard_batches, shared_permutation
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    flat = FlatGradAllReduce(model.parameters())
+    perm = shared_permutation(20, seed=7, epoch=1)
+    mine = shard_batches(10, rank, world)
+    data = torch.arange(80, dtype=torch.float32).reshape(20, 4)
+    losses = []
+    for b in mine[:2]:
+        idx = perm[b * 2:(b + 1) * 2]
+        flat.zero()
+        loss = model(data[idx]).sum()
+        loss.backward()
+        flat.check_views()
+        local = flat.flat.clone()
+        flat.allreduce_mean()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(flat.flat, sum(gathered) / world)
+        losses.append(float(loss))
+    out[rank] = (perm.tolist(), mine, flat.flat.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_label_batch_dp_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29531, out), nprocs=world, join=True)
+    (p0, b0, g0), (p1, b1, g1) = out[0], out[1]
+    assert p0 == p1                                     # one shared order, no communication
+    assert b0 == [0, 2, 4, 6, 8] and b1 == [1, 3, 5, 7, 9]
+    assert g0 == g1                                     # averaged gradients identical on both ranks
+
+
+def test_shard_batches_drops_remainder():
+    from glass_b200.dist import shard_batches
+    assert shard_batches(7, 0, 2) == [0, 2, 4] and shard_batches(7, 1, 2) == [1, 3, 5]
+    assert shard_batches(5, 0, 1) == [0, 1, 2, 3, 4]
+    assert shard_batches(3, 3, 4) == []
