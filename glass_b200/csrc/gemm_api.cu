@@ -84,8 +84,7 @@ extern "C" int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const 
         return GLASS_OK;
     }
     // dX goes through tcgen05 when the shape allows; dW/db (reduction over rows) stay on the SIMT split-N kernel.
-    const bool tc_ok = pair_tc_supported(2 * h, 0, (k1 + k2 + 1) / 2, lddo, 0, dout, nullptr) && k2 >= 0 &&
-                       (k1 + k2) % 16 == 0;
+    const bool tc_ok = pair_tc_supported(k1, k2, h, lda1, lda2, a1, a2);
     if (path == GLASS_GEMM_TCGEN05 && !tc_ok) {
         set_error("pair_linear_mix_bwd: tcgen05 path does not support k1=%d k2=%d h=%d", k1, k2, h);
         return GLASS_ERR_UNSUPPORTED;

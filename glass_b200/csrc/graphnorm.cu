@@ -17,7 +17,7 @@ namespace glass {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxPartialCtas = 592;  // 4 CTAs per SM on 148 SMs; fixed so the workspace size is device independent
+constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs; fixed so the workspace size is device independent
 
 // stats rows
 enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4 };
@@ -105,16 +105,28 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
     }
 }
 
-__global__ void k_gn_finalize_fwd(const double* __restrict__ partial, int nblk, int64_t n, int c,
-                                  const float* __restrict__ weight, const float* __restrict__ bias,
-                                  const float* __restrict__ mean_scale, float eps, float* __restrict__ stats) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= c) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblk; ++b) {
+// One warp per column: lane l adds partials l, l+32, ... in order, then a fixed butterfly -> deterministic.
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int nblk, int c, int col,
+                                                double& s, double& q) {
+    const int lane = threadIdx.x & 31;
+    s = 0.0;
+    q = 0.0;
+    for (int b = lane; b < nblk; b += 32) {
         s += partial[((int64_t)b * 2 + 0) * c + col];
         q += partial[((int64_t)b * 2 + 1) * c + col];
     }
+    s = warp_sum(s);
+    q = warp_sum(q);
+}
+
+__global__ void k_gn_finalize_fwd(const double* __restrict__ partial, int nblk, int64_t n, int c,
+                                  const float* __restrict__ weight, const float* __restrict__ bias,
+                                  const float* __restrict__ mean_scale, float eps, float* __restrict__ stats) {
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= c) return;
+    double s, q;
+    reduce_partials(partial, nblk, c, col, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     const double mu = s / (double)n, ex2 = q / (double)n;
     const float muf = (float)mu;
     const float am = __fmul_rn(muf, mean_scale[col]);  // mean * mean_scale, rounded like the reference
@@ -164,13 +176,11 @@ __global__ void k_gn_finalize_bwd(const double* __restrict__ partial, int nblk, 
                                   const float* __restrict__ weight, const float* __restrict__ mean_scale,
                                   const float* __restrict__ stats, float* __restrict__ coef, float* __restrict__ dweight,
                                   float* __restrict__ dbias, float* __restrict__ dmean_scale) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (col >= c) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        s1 += partial[((int64_t)b * 2 + 0) * c + col];
-        s2 += partial[((int64_t)b * 2 + 1) * c + col];
-    }
+    double s1, s2;
+    reduce_partials(partial, nblk, c, col, s1, s2);
+    if ((threadIdx.x & 31) != 0) return;
     const double w = weight[col], a = mean_scale[col];
     const double rstd = stats[ST_RSTD * c + col], mu = stats[ST_MU * c + col], am = stats[ST_AM * c + col];
     const double N = (double)n;
@@ -262,7 +272,7 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
     else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
-    k_gn_finalize_fwd<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nblk, n, c, weight, bias, mean_scale, eps, stats);
+    k_gn_finalize_fwd<<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, weight, bias, mean_scale, eps, stats);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
     if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, keep, pscale, out, ldo, n, c);
@@ -292,7 +302,7 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
     else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
-    k_gn_finalize_bwd<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(partial, nblk, n, c, weight, mean_scale, stats, coef,
+    k_gn_finalize_bwd<<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, weight, mean_scale, stats, coef,
                                                                dweight, dbias, dmean_scale);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);

@@ -1,8 +1,8 @@
 // Padded-subgraph pooling: GLASS.Pool (reference impl/models.py:346-350) = pad2batch + emb[pos] gather +
 // Add/Mean/Max/Size pool (impl/models.py:295-319, PyG global_*_pool / GraphSizeNorm).
 // One CTA per subgraph walks its padded row (skipping -1) so neither the (batch, pos) vectors nor the
-// gathered [n_valid, D] matrix are ever materialised.  Rows are accumulated in pad order = the order of
-// the reference's index_add, so sums match a sequential CPU loop.
+// gathered [n_valid, D] matrix are ever materialised.  The CTA is 2-D (columns x row lanes): each row lane
+// sums every LQ-th row in pad order, the lane partials are combined in lane order (deterministic).
 // Algorithmic bytes: 8*B*Lmax (ids) + 4*D*n_valid (gathered rows) + 4*B*D (output).
 #include <float.h>
 
@@ -40,44 +40,75 @@ struct BatchSeg {  // rows already gathered; batch sorted ascending -> segment =
     }
 };
 
+// CTA = CT column threads x LQ row lanes (CT*LQ <= 1024).  Row lane q accumulates rows q, q+LQ, ... of the
+// segment (independent loads, ~len/LQ deep instead of len deep), then lane 0 combines the LQ partials in
+// lane order.  MAX keeps (value, position) and resolves ties towards the earliest position.
+constexpr int kPoolMaxThreads = 1024;
+
 template <class RowFn>
 __device__ __forceinline__ void pool_fwd_body(RowFn row_of, int64_t len, const float* __restrict__ emb, int64_t lde,
                                               int mode, float* __restrict__ out, float* __restrict__ cnt_out,
                                               int32_t* __restrict__ argmax, int d, int64_t b) {
-    __shared__ float s_cnt;
-    if (threadIdx.x == 0) {
+    __shared__ int s_cnt;
+    __shared__ float s_val[kPoolMaxThreads];
+    __shared__ int s_pos[kPoolMaxThreads];
+    const int CT = blockDim.x, LQ = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+    if (tx == 0 && ty == 0) s_cnt = 0;
+    __syncthreads();
+    if (tx == 0) {
         int c = 0;
-        for (int64_t l = 0; l < len; ++l) c += row_of(l) >= 0;
-        s_cnt = (float)c;
-        if (cnt_out) cnt_out[b] = (float)c;
+        for (int64_t l = ty; l < len; l += LQ) c += row_of(l) >= 0;
+        if (c) atomicAdd(&s_cnt, c);
     }
     __syncthreads();
-    const float cnt = s_cnt;
+    const float cnt = (float)s_cnt;
+    if (tx == 0 && ty == 0 && cnt_out) cnt_out[b] = cnt;
     const float coef = (mode == GLASS_POOL_SIZE && cnt > 0.f) ? size_coef(cnt) : 1.f;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    for (int c0 = 0; c0 < d; c0 += CT) {
+        const int c = c0 + tx;
         float acc = (mode == GLASS_POOL_MAX) ? -FLT_MAX : 0.f;
-        int32_t arg = -1;
-        for (int64_t l = 0; l < len; ++l) {
-            const int64_t r = row_of(l);
-            if (r < 0) continue;
-            const float v = emb[r * lde + c];
-            if (mode == GLASS_POOL_MAX) {
-                if (arg < 0 || v > acc) {
-                    acc = v;
-                    arg = (int32_t)(mode == GLASS_POOL_MAX ? r : 0);
+        int best = -1;
+        if (c < d) {
+            for (int64_t l = ty; l < len; l += LQ) {
+                const int64_t r = row_of(l);
+                if (r < 0) continue;
+                const float v = emb[r * lde + c];
+                if (mode == GLASS_POOL_MAX) {
+                    if (best < 0 || v > acc) {
+                        acc = v;
+                        best = (int)l;
+                    }
+                } else if (mode == GLASS_POOL_SIZE) {
+                    acc = __fadd_rn(acc, __fmul_rn(v, coef));
+                } else {
+                    acc += v;
                 }
-            } else if (mode == GLASS_POOL_SIZE) {
-                acc = __fadd_rn(acc, __fmul_rn(v, coef));
-            } else {
-                acc += v;
             }
         }
-        if (mode == GLASS_POOL_MEAN) acc = acc / fmaxf(cnt, 1.f);
-        if (mode == GLASS_POOL_MAX) {
-            if (arg < 0) acc = 0.f;  // empty segment -> 0 (PyG scatter semantics)
-            if (argmax) argmax[b * (int64_t)d + c] = arg;
+        s_val[ty * CT + tx] = acc;
+        s_pos[ty * CT + tx] = best;
+        __syncthreads();
+        if (ty == 0 && c < d) {
+            for (int q = 1; q < LQ; ++q) {
+                const float v = s_val[q * CT + tx];
+                const int p = s_pos[q * CT + tx];
+                if (mode == GLASS_POOL_MAX) {
+                    if (p >= 0 && (best < 0 || v > acc || (v == acc && p < best))) {
+                        acc = v;
+                        best = p;
+                    }
+                } else {
+                    acc += v;
+                }
+            }
+            if (mode == GLASS_POOL_MEAN) acc = acc / fmaxf(cnt, 1.f);
+            if (mode == GLASS_POOL_MAX) {
+                if (best < 0) acc = 0.f;  // empty segment -> 0 (PyG scatter semantics)
+                if (argmax) argmax[b * (int64_t)d + c] = best < 0 ? -1 : (int32_t)row_of(best);
+            }
+            out[c] = acc;
         }
-        out[c] = acc;
+        __syncthreads();
     }
 }
 
@@ -106,15 +137,18 @@ __global__ void k_pool_pad_bwd(const float* __restrict__ dout, int64_t lddo, Pad
                                const float* __restrict__ cnt, const int32_t* __restrict__ argmax,
                                float* __restrict__ demb, int64_t ldde, int d) {
     const int64_t b = blockIdx.x;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const int CT = blockDim.x, LQ = blockDim.y;
+    for (int c = threadIdx.x; c < d; c += CT) {
         const float g = dout[b * lddo + c];
         if (mode == GLASS_POOL_MAX) {
-            const int32_t a = argmax[b * (int64_t)d + c];
-            if (a >= 0) atomicAdd(demb + (int64_t)a * ldde + c, g);
+            if (threadIdx.y == 0) {
+                const int32_t a = argmax[b * (int64_t)d + c];
+                if (a >= 0) atomicAdd(demb + (int64_t)a * ldde + c, g);
+            }
             continue;
         }
         const float gc = g * bwd_coef(mode, cnt[b]);
-        for (int64_t l = 0; l < seg.lmax; ++l) {
+        for (int64_t l = threadIdx.y; l < seg.lmax; l += LQ) {
             const int64_t r = seg.row(b, l);
             if (r >= 0) atomicAdd(demb + r * ldde + c, gc);  // nodes may belong to several subgraphs
         }
@@ -137,7 +171,10 @@ __global__ void k_pool_batch_bwd(const float* __restrict__ dout, int64_t lddo, c
     }
 }
 
-inline int pool_threads(int d) { return d <= 32 ? 32 : (d >= 256 ? 256 : (d + 31) / 32 * 32); }
+inline dim3 pool_block(int d) {
+    int ct = d <= 32 ? 32 : (d >= 128 ? 128 : (d + 31) / 32 * 32);
+    return dim3(ct, kPoolMaxThreads / ct >= 1 ? (kPoolMaxThreads / ct > 32 ? 32 : kPoolMaxThreads / ct) : 1);
+}
 inline bool mode_ok(int mode) { return mode >= GLASS_POOL_SUM && mode <= GLASS_POOL_SIZE; }
 
 }  // namespace
@@ -157,7 +194,7 @@ extern "C" int glass_segment_pool_fwd(const float* emb, int64_t lde, const int64
     GLASS_CHECK_ARG(mode != GLASS_POOL_MAX || argmax, "segment_pool_fwd: MAX needs argmax");
     if (b == 0) return GLASS_OK;
     PadSeg seg{pos, lmax, n_node};
-    k_pool_pad_fwd<<<(unsigned)b, pool_threads(d), 0, as_stream(stream)>>>(emb, lde, seg, mode, out, ldo, cnt, argmax, d);
+    k_pool_pad_fwd<<<(unsigned)b, pool_block(d), 0, as_stream(stream)>>>(emb, lde, seg, mode, out, ldo, cnt, argmax, d);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }
@@ -174,7 +211,7 @@ extern "C" int glass_segment_pool_bwd(const float* dout, int64_t lddo, const int
     GLASS_CHECK_ARG(mode != GLASS_POOL_MAX || argmax, "segment_pool_bwd: MAX needs argmax");
     if (b == 0) return GLASS_OK;
     PadSeg seg{pos, lmax, n_node};
-    k_pool_pad_bwd<<<(unsigned)b, pool_threads(d), 0, as_stream(stream)>>>(dout, lddo, seg, mode, cnt, argmax, demb, ldde, d);
+    k_pool_pad_bwd<<<(unsigned)b, pool_block(d), 0, as_stream(stream)>>>(dout, lddo, seg, mode, cnt, argmax, demb, ldde, d);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }
@@ -191,7 +228,7 @@ extern "C" int glass_segment_pool_batch_fwd(const float* x, int64_t ldx, const i
     GLASS_CHECK_ARG(mode != GLASS_POOL_MAX || argmax, "segment_pool_batch_fwd: MAX needs argmax");
     if (n_seg == 0) return GLASS_OK;
     BatchSeg seg{batch, m};
-    k_pool_batch_fwd<<<(unsigned)n_seg, pool_threads(d), 0, as_stream(stream)>>>(x, ldx, seg, mode, out, ldo, cnt, argmax, d);
+    k_pool_batch_fwd<<<(unsigned)n_seg, pool_block(d), 0, as_stream(stream)>>>(x, ldx, seg, mode, out, ldo, cnt, argmax, d);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

@@ -28,10 +28,14 @@ class GraphedTrainStep:
         self.y = torch.empty_like(y_example, device=dev)
         self.pos.copy_(pos_example)
         self.y.copy_(y_example)
-        self.flat = FlatGradAllReduce(model.parameters(), group)
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # one flat gradient buffer (single all-reduce) only when there is something to reduce; on one GPU
+        # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate pass)
+        self.flat = FlatGradAllReduce(model.parameters(), group) if world > 1 else None
         self.lr = torch.tensor(float(lr), device=dev)
         self.opt = torch.optim.Adam(model.parameters(), lr=self.lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                                    capturable=True, foreach=True)
+                                    capturable=True, fused=True)
         self.loss = torch.zeros((), device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         model.train()
@@ -47,10 +51,14 @@ class GraphedTrainStep:
     # one iteration of impl/train.py:10-16
     def _step_eager(self):
         z = self.z_fn(self.x, self.pos)
-        self.flat.zero()
+        if self.flat is None:
+            self.opt.zero_grad(set_to_none=True)
+        else:
+            self.flat.zero()
         loss = self.loss_fn(self.model(self.x, self.ei, self.ew, self.pos, z, id=0), self.y)
         loss.backward()
-        self.flat.allreduce_mean()
+        if self.flat is not None:
+            self.flat.allreduce_mean()
         self.opt.step()
         self.loss.copy_(loss.detach())
 
@@ -60,7 +68,8 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step_eager()
-        self.flat.check_views()
+        if self.flat is not None:
+            self.flat.check_views()
         return self
 
     def reset_to(self, state_dict):

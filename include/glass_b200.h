@@ -137,8 +137,8 @@ int glass_embedding_bwd(const float* dout, int64_t lddo, const int64_t* ids, flo
 /* ------------------------------------------------------------------------------------------
  * Padded-subgraph pooling (GLASS.Pool impl/models.py:346-350 = pad2batch + emb[pos] + pool_fn;
  * pools impl/models.py:295-319).  pos int64 [b, lmax], -1 = padding.  One CTA per subgraph reads
- * the padded row directly; rows are accumulated in pad order (same order as the reference's
- * index_add).  out [b, d]; cnt fp32 [b] (valid nodes per row); argmax int32 [b, d] (MAX only,
+ * the padded row directly; row lanes accumulate strided rows in pad order and are combined in a
+ * fixed order (deterministic).  out [b, d]; cnt fp32 [b] (valid nodes per row); argmax int32 [b, d] (MAX only,
  * else may be NULL): node id of the first maximum, -1 for an empty row.
  * bwd ACCUMULATES into demb [n_node, d] (caller zero-fills) with atomics.
  * ------------------------------------------------------------------------------------------ */
