@@ -1,0 +1,22 @@
+"""GPU: launch each pair-GEMM variant a few times (for an ncu duration listing)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from glass_b200 import _lib, ops
+torch.cuda.set_device(0)
+dev = "cuda:0"
+n = 57333
+for (k1, k2, h, act) in [(64, 0, 64, 2), (64, 64, 64, 0)]:
+    g = torch.Generator().manual_seed(0)
+    a1 = torch.randn(n, k1, generator=g).to(dev).requires_grad_(True)
+    a2 = torch.randn(n, k2, generator=g).to(dev).requires_grad_(True) if k2 else None
+    k = k1 + k2
+    w0 = torch.randn(h, k).to(dev).requires_grad_(True); w1 = torch.randn(h, k).to(dev).requires_grad_(True)
+    b0 = torch.randn(h).to(dev).requires_grad_(True); b1 = torch.randn(h).to(dev).requires_grad_(True)
+    mask = (torch.rand(n) > 0.5).to(torch.uint8).to(dev)
+    gout = torch.randn(n, h).to(dev)
+    for pid in (_lib.GEMM_SIMT, _lib.GEMM_TCGEN05):
+        for _ in range(3):
+            out = ops.pair_linear_mix(a1, a2, w0, b0, w1, b1, mask, 0.8, act, pid)
+            out.backward(gout)
+    torch.cuda.synchronize()

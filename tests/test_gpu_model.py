@@ -28,6 +28,15 @@ def _product_from_case(c, dropout=0.0):
     return m.to(DEV)
 
 
+def _grad_tol(k, c):
+    """--use_one: every node has the same input row, so emb_gn sees zero variance and its output (and the
+    gradients of input_emb / emb_gn) are rounding noise amplified by 1/sqrt(eps) in ANY implementation
+    (DESIGN.md "parity limits"); they are compared loosely.  Everything else: the 1e-4 bar."""
+    if c["raw"]["emb"] == "one" and ("input_emb" in k or "emb_gn" in k):
+        return 2e-2
+    return TOL
+
+
 def _dev(c):
     z = c["z"].to(DEV) if c["z"] is not None else None
     return c["x"].to(DEV), c["ei"].to(DEV), c["ew"].to(DEV), c["pos"].to(DEV), z
@@ -57,8 +66,7 @@ def test_gradients_match_reference_golden(name):
     loss.backward()
     assert abs(float(loss) - c["loss"]) < TOL * max(1.0, abs(c["loss"]))
     for k, p in m.named_parameters():
-        # --use_one: the embedding gradient is rounding noise amplified by emb_gn
-        tol = 2e-2 if ("input_emb" in k and c["raw"]["emb"] == "one") else TOL
+        tol = _grad_tol(k, c)
         assert rel_err(p.grad.cpu(), c["grads"][k]) < tol, k
 
 
@@ -84,8 +92,7 @@ def test_train_mode_with_injected_dropout_masks_matches_oracle(name):
     loss.backward()
     assert rel_err(logits.detach().cpu(), ref_logits.detach()) < TOL
     for k, prm in m.named_parameters():
-        tol = 2e-2 if ("input_emb" in k and c["raw"]["emb"] == "one") else TOL
-        assert rel_err(prm.grad.cpu(), sd[k].grad) < tol, k
+        assert rel_err(prm.grad.cpu(), sd[k].grad) < _grad_tol(k, c), k
 
 
 def test_generic_pool_path_and_poolmodule_api():
