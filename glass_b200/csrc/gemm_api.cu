@@ -17,6 +17,11 @@ bool pair_tc_supported(int k1, int k2, int h, int64_t lda1, int64_t lda2, const 
 int pair_fwd_tc(const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2, int k2, const float* w0,
                 const float* b0, const float* w1, const float* b1, const uint8_t* mask, float z, int act, float* out,
                 int64_t ldo, float* acts, int64_t n, int h, cudaStream_t st);
+bool pair_dw_tc_supported(int k1, int k2, int h, int64_t lda1, int64_t lda2, const void* a1, const void* a2);
+size_t pair_dw_tc_workspace_bytes(int64_t n, int h, int k);
+int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const float* a1, int64_t lda1, int k1,
+                   const float* a2, int64_t lda2, int k2, const uint8_t* mask, float z, int act, float* dw0, float* db0,
+                   float* dw1, float* db1, int64_t n, int h, void* workspace, cudaStream_t st);
 int pair_bwd_dx_tc(const float* dout, int64_t lddo, const float* acts, const float* w0, const float* w1,
                    const uint8_t* mask, float z, int act, float* da1, int64_t ldda1, int k1, float* da2, int64_t ldda2,
                    int k2, int64_t n, int h, cudaStream_t st);
@@ -58,7 +63,9 @@ extern "C" int glass_pair_linear_mix_fwd(const float* a1, int64_t lda1, int k1, 
 
 extern "C" size_t glass_pair_linear_mix_bwd_workspace_bytes(int64_t n, int h, int k) {
     if (n < 0 || h <= 0 || k <= 0) return 0;
-    return align_up((size_t)dw_splits(n, h, k) * 2 * (size_t)h * ((size_t)k + 1) * sizeof(float), 256);
+    size_t simt = (size_t)dw_splits(n, h, k) * 2 * (size_t)h * ((size_t)k + 1) * sizeof(float);
+    size_t tc = pair_dw_tc_workspace_bytes(n, h, k);
+    return align_up(simt > tc ? simt : tc, 256);
 }
 
 extern "C" int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts, const float* a1,
@@ -97,6 +104,16 @@ extern "C" int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const 
         if (rc != GLASS_OK) return rc;
         da1_s = nullptr;
         da2_s = nullptr;
+    }
+    if ((path == GLASS_GEMM_TCGEN05 || path == GLASS_GEMM_AUTO) && tc_ok &&
+        pair_dw_tc_supported(k1, k2, h, lda1, lda2, a1, a2)) {
+        if (da1_s || da2_s) {   // (not reached: dX already went through tcgen05 above)
+            int rc = pair_bwd_simt(dout, lddo, acts, a1, lda1, k1, a2, lda2, k2, w0, w1, mask, z_ratio, act, da1_s,
+                                   ldda1, da2_s, ldda2, dw0, db0, dw1, db1, n, h, workspace, st);
+            if (rc != GLASS_OK) return rc;
+        }
+        return pair_bwd_dw_tc(dout, lddo, act == GLASS_ACT_NONE ? nullptr : acts, a1, lda1, k1, a2, lda2, k2, mask,
+                              z_ratio, act, dw0, db0, dw1, db1, n, h, workspace, st);
     }
     return pair_bwd_simt(dout, lddo, acts, a1, lda1, k1, a2, lda2, k2, w0, w1, mask, z_ratio, act, da1_s, ldda1, da2_s,
                          ldda2, dw0, db0, dw1, db1, n, h, workspace, st);

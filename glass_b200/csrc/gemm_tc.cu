@@ -9,11 +9,13 @@
 // far inside the 1e-4 bar (the dropped Alo*Blo term is ~2^-22).  K <= 256, so the GEMM is HBM-bound even at
 // 3x the MMA count.
 //
-// CTA = 13 warps, persistent over 128-row tiles (grid = #SMs):
-//   warps 0-3  epilogue: tcgen05.ld (TMEM lane = row) -> bias/act/mix -> global
-//   warp  4    TMEM allocator; lane 0 issues tcgen05.mma / tcgen05.commit
-//   warps 5-12 operand loader: coalesced float4 global loads -> hi/lo split -> st.shared into the
-//              128B-swizzled K-major UMMA layout -> fence.proxy.async -> mbarrier arrive
+// CTA = 17 warps, persistent over 128-row tiles (grid = #SMs):
+//   warps 0-7  epilogue: tcgen05.ld (TMEM lane = row; warp w reads lane quadrant w % 4, warps w and w+4
+//              split the columns) -> bias/act/mix -> global
+//   warp  8    TMEM allocator; lane 0 issues tcgen05.mma / tcgen05.commit
+//   warps 9-16 operand loader: coalesced float4 global loads kept in a register ring 2-3 K-blocks deep
+//              -> hi/lo split -> st.shared into the 128B-swizzled K-major UMMA layout ->
+//              fence.proxy.async -> mbarrier arrive
 // The weight operand (both weight sets, hi and lo) stays resident in shared memory for the CTA's lifetime;
 // the row operand streams through a ring of 32-float K-blocks.  Two accumulators (2 x N TMEM columns)
 // overlap the epilogue of tile i with the MMAs of tile i+1.
@@ -24,7 +26,7 @@ namespace {
 
 constexpr int BM = 128;                 // rows per tile == UMMA M (TMEM lane == row)
 constexpr int KBF = 32;                 // floats per K-block == one 128-byte swizzle row
-constexpr int kEpiWarps = 4, kLoadWarps = 8;
+constexpr int kEpiWarps = 8, kLoadWarps = 8;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;
 constexpr int kStageBytes = BM * 128 * 2;   // hi + lo tile of one K-block
@@ -233,9 +235,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             const int acc = it & 1;
             mbar_wait(smem_u32(tfull + acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int64_t row = tile * BM + warp * 32 + lane;
+            const int quad = warp & 3, half = warp >> 2;         // TMEM lane quadrant (== warp % 4), column half
+            const int64_t row = tile * BM + quad * 32 + lane;
             const bool row_ok = row < P.n;
-            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N);
             if (!BWD) {
                 float c0 = 0.f, c1 = 0.f;
                 if (row_ok) {
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     c1 = lab ? P.z : 1.f - P.z;
                     c0 = lab ? 1.f - P.z : P.z;
                 }
-                for (int c = 0; c < H; c += 8) {
+                for (int c = half * 8; c < H; c += 16) {
                     float p0[8], p1[8];
                     tmem_ld8(t_row + (uint32_t)c, p0);
                     tmem_ld8(t_row + (uint32_t)(H + c), p1);
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     }
                 }
             } else {
-                for (int c = 0; c < N; c += 8) {
+                for (int c = half * 8; c < N; c += 16) {
                     float d[8];
                     tmem_ld8(t_row + (uint32_t)c, d);
                     tmem_ld_wait();
@@ -330,56 +333,84 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     } else {
         // ================================ operand loader ====================================
         const int lt = threadIdx.x - (kEpiWarps + 1) * 32;                 // 0 .. 255
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                float4 v[4];
+        const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t total = my_tiles * nkb;                              // K-blocks this CTA streams
+        constexpr int D = BWD ? 2 : 3;                                     // register ring depth (K-blocks in flight)
+        struct Raw {
+            float4 g[4];
+            float4 a[BWD ? 4 : 1];
+            float coef[BWD ? 4 : 1];
+        };
+        Raw ring[D];
+
+        auto issue = [&](int64_t seq, Raw& rw) {
+            const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
+            const int kb = (int)(seq % nkb);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = lt + i * kLoadThreads;
-                    const int r = q >> 3, ch = q & 7;
-                    const int64_t row = tile * BM + r;
-                    const int k = kb * KBF + ch * 4;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < P.n && k < K) {
-                        if (!BWD) {
-                            v[i] = (k < P.k1) ? ldg_f4(P.a1 + row * P.lda1 + k) : ldg_f4(P.a2 + row * P.lda2 + (k - P.k1));
-                        } else {
-                            // dP[row][k..k+3]: k indexes the 2H pre-activation columns (branch 0 | branch 1)
-                            const int br = k >= H;
-                            const int c = k - br * H;
-                            const uint8_t lab = P.mask[row];
-                            const float coef = (lab != 0) == (br != 0) ? P.z : 1.f - P.z;
-                            float4 g = ldg_f4(P.dout + row * P.lddo + c);
-                            g.x *= coef, g.y *= coef, g.z *= coef, g.w *= coef;
-                            if (P.acts) {
-                                const float4 a = ldg_f4(P.acts + row * (2 * (int64_t)H) + k);
-                                g.x *= act_grad_from_out(a.x, P.act);
-                                g.y *= act_grad_from_out(a.y, P.act);
-                                g.z *= act_grad_from_out(a.z, P.act);
-                                g.w *= act_grad_from_out(a.w, P.act);
-                            }
-                            v[i] = g;
-                        }
+            for (int i = 0; i < 4; ++i) {
+                const int q = lt + i * kLoadThreads;
+                const int r = q >> 3, ch = q & 7;
+                const int64_t row = tile * BM + r;
+                const int k = kb * KBF + ch * 4;
+                rw.g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BWD) {
+                    rw.a[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    rw.coef[i] = 0.f;
+                }
+                if (row < P.n && k < K) {
+                    if (!BWD) {
+                        rw.g[i] = (k < P.k1) ? ldg_f4(P.a1 + row * P.lda1 + k) : ldg_f4(P.a2 + row * P.lda2 + (k - P.k1));
+                    } else {
+                        // dP[row][k..k+3]: k indexes the 2H pre-activation columns (branch 0 | branch 1)
+                        const int br = k >= H;
+                        rw.g[i] = ldg_f4(P.dout + row * P.lddo + (k - br * H));
+                        if (P.acts) rw.a[i] = ldg_f4(P.acts + row * (2 * (int64_t)H) + k);
+                        rw.coef[i] = ((P.mask[row] != 0) == (br != 0)) ? P.z : 1.f - P.z;
                     }
                 }
-                mbar_wait(smem_u32(empty + stage), phase ^ 1);
-                uint8_t* dst = a_ring + (size_t)stage * kStageBytes;
+            }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        auto consume = [&](const Raw& rw) {
+            mbar_wait(smem_u32(empty + stage), phase ^ 1);
+            uint8_t* dst = a_ring + (size_t)stage * kStageBytes;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = lt + i * kLoadThreads;
-                    const uint32_t off = swz(q >> 3, q & 7);
-                    float4 hi, lo;
-                    split_tf32(v[i], hi, lo);
-                    *reinterpret_cast<float4*>(dst + off) = hi;
-                    *reinterpret_cast<float4*>(dst + BM * 128 + off) = lo;
+            for (int i = 0; i < 4; ++i) {
+                const int q = lt + i * kLoadThreads;
+                const uint32_t off = swz(q >> 3, q & 7);
+                float4 v = rw.g[i];
+                if (BWD) {
+                    const float c = rw.coef[i];
+                    v.x *= c, v.y *= c, v.z *= c, v.w *= c;
+                    if (P.acts) {
+                        v.x *= act_grad_from_out(rw.a[i].x, P.act);
+                        v.y *= act_grad_from_out(rw.a[i].y, P.act);
+                        v.z *= act_grad_from_out(rw.a[i].z, P.act);
+                        v.w *= act_grad_from_out(rw.a[i].w, P.act);
+                    }
                 }
-                fence_proxy_async();
-                mbar_arrive(smem_u32(full + stage));
-                if (++stage == P.stages) {
-                    stage = 0;
-                    phase ^= 1;
+                float4 hi, lo;
+                split_tf32(v, hi, lo);
+                *reinterpret_cast<float4*>(dst + off) = hi;
+                *reinterpret_cast<float4*>(dst + BM * 128 + off) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(full + stage));
+            if (++stage == P.stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            if (d < total) issue(d, ring[d]);
+        for (int64_t seq = 0; seq < total; seq += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (seq + d < total) {
+                    consume(ring[d]);
+                    if (seq + d + D < total) issue(seq + d + D, ring[d]);
                 }
             }
         }
@@ -390,6 +421,256 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     __syncthreads();
     tc_fence_after();
     if (warp == kEpiWarps) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW / db on tensor cores:  dWcat[2H x K] = dP^T[2H x n] * A[n x K],  db = column sums of dP.
+// The reduction runs over graph rows, so both operands are MN-major in their natural row-major global
+// layout (dP[i][j], A[i][k]: the non-reduction index is contiguous).  Each stage holds 32 rows i:
+//   operand tile = MN-atoms of 32 elements (128 B) x 8 rows (1024 B, 128B swizzle on the row index),
+//   4 row-groups per atom column (SBO = 1024), atom columns 4096 B apart (LBO = 4096)
+// (canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) of the UMMA MN-major descriptor).
+// CTA s reduces rows [s*R, (s+1)*R) into one TMEM accumulator and writes part[s]; a second kernel sums
+// the partials in CTA order (deterministic).  21 warps: 0-3 epilogue, 4 MMA, 5-20 loaders.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwLoadWarps = 16, kDwLoadThreads = kDwLoadWarps * 32, kDwEpiWarps = 4;
+constexpr int kDwThreads = (kDwEpiWarps + 1 + kDwLoadWarps) * 32;
+constexpr int kDwRows = 32;                    // reduction rows per stage
+
+struct DwParams {
+    const float* dout;
+    int64_t lddo;
+    const float* acts;
+    const uint8_t* mask;
+    float z;
+    int act;
+    int h;
+    const float* a1;
+    int64_t lda1;
+    int k1;
+    const float* a2;
+    int64_t lda2;
+    int k2;
+    int64_t n;
+    float* part;          // [splits][2h][part_ld]; column K holds the db partial
+    int part_ld;
+    int64_t rows_per_cta; // multiple of 32
+    int stages;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;               // LBO: next 32-element atom column
+    d |= (uint64_t)(1024 >> 4) << 32;               // SBO: next group of 8 reduction rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// element chunk (4 consecutive MN elements starting at `mn`, reduction row `i` of the stage)
+__device__ __forceinline__ uint32_t swz_mn(int mn, int i) {
+    return (uint32_t)((mn >> 5) * 4096 + (i >> 3) * 1024 + (i & 7) * 128 + ((((mn & 31) >> 2) ^ (i & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = P.h, K = P.k1 + P.k2;
+    const int j0 = blockIdx.y * 128;                          // 128-row slice of the 2H outputs
+    const int a_bytes = 128 * 128;                            // 128 j x 32 rows x 4 B
+    const int b_bytes = K * 128;
+    const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + P.stages;
+    uint64_t* tfull = bars + 2 * P.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    float* s_db = reinterpret_cast<float*>(tmem_slot + 4);   // [16][128]
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(smem_u32(full + s), kDwLoadThreads);
+            mbar_init(smem_u32(empty + s), 1);
+        }
+        mbar_init(smem_u32(tfull), 1);
+        fence_barrier_init();
+    }
+    if (warp == kDwEpiWarps) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t m_lo = (int64_t)blockIdx.x * P.rows_per_cta;
+    const int64_t m_hi = min(m_lo + P.rows_per_cta, P.n);
+    const int64_t total = m_hi > m_lo ? (m_hi - m_lo + kDwRows - 1) / kDwRows : 0;   // stages to stream
+
+    if (warp < kDwEpiWarps) {
+        // -------- epilogue (after the whole reduction) --------
+        if (total > 0) {
+            mbar_wait(smem_u32(tfull), 0);
+            tc_fence_after();
+        }
+        const int j = warp * 32 + lane;
+        float* dst = P.part + ((int64_t)blockIdx.x * (2 * H) + j0 + j) * P.part_ld;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < K; c += 8) {
+            float d[8];
+            if (total > 0) {
+                tmem_ld8(t_row + (uint32_t)c, d);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d[u] = 0.f;
+            }
+            reinterpret_cast<float4*>(dst + c)[0] = make_float4(d[0], d[1], d[2], d[3]);
+            reinterpret_cast<float4*>(dst + c)[1] = make_float4(d[4], d[5], d[6], d[7]);
+        }
+        tc_fence_before();
+    } else if (warp == kDwEpiWarps) {
+        // -------- MMA issuer --------
+        if (lane == 0 && total > 0) {
+            const uint32_t idesc = make_idesc(128, K) | (1u << 15) | (1u << 16);   // both operands MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t st = 0; st < total; ++st) {
+                mbar_wait(smem_u32(full + stage), phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_lo = a_hi + a_bytes;
+                const uint32_t b_hi = a_lo + a_bytes;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int kg = 0; kg < 4; ++kg) {
+                    const uint64_t dah = make_smem_desc_mn(a_hi + kg * 1024), dal = make_smem_desc_mn(a_lo + kg * 1024);
+                    const uint64_t dbh = make_smem_desc_mn(b_hi + kg * 1024), dbl = make_smem_desc_mn(b_lo + kg * 1024);
+                    umma_tf32(tmem_base, dal, dbh, idesc, (st | kg) ? 1u : 0u);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                }
+                umma_commit(smem_u32(empty + stage));
+                if (++stage == P.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(smem_u32(tfull));
+        }
+    } else {
+        // -------- loaders: straight row-major copies into the MN-major tiles --------
+        const int lt = threadIdx.x - (kDwEpiWarps + 1) * 32;        // 0 .. 511
+        const int jc = (lt & 31) * 4;                                // this thread's 4 dP columns (fixed)
+        const int j = j0 + jc;
+        const int br = j >= H;
+        const int kchunks = K >> 2;                                  // float4 chunks per A row
+        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        struct Raw {
+            float4 g[2], a[2], x[2];
+            float coef[2];
+        };
+        Raw ring[2];
+        auto issue = [&](int64_t st, Raw& rw) {
+            const int64_t r0 = m_lo + st * kDwRows;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int i = (lt >> 5) + 16 * t;
+                const int64_t row = r0 + i;
+                rw.g[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rw.a[t] = make_float4(1.f, 1.f, 1.f, 1.f);
+                rw.coef[t] = 0.f;
+                if (row < m_hi) {
+                    rw.g[t] = ldg_f4(P.dout + row * P.lddo + (j - br * H));
+                    if (P.acts) rw.a[t] = ldg_f4(P.acts + row * (2 * (int64_t)H) + j);
+                    rw.coef[t] = ((P.mask[row] != 0) == (br != 0)) ? P.z : 1.f - P.z;
+                }
+                const int q = lt + t * kDwLoadThreads;
+                rw.x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < kDwRows * kchunks) {
+                    const int ib = q / kchunks, k = (q % kchunks) * 4;
+                    const int64_t rowb = r0 + ib;
+                    if (rowb < m_hi) rw.x[t] = (k < P.k1) ? ldg_f4(P.a1 + rowb * P.lda1 + k) : ldg_f4(P.a2 + rowb * P.lda2 + (k - P.k1));
+                }
+            }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        auto consume = [&](const Raw& rw) {
+            mbar_wait(smem_u32(empty + stage), phase ^ 1);
+            uint8_t* base = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int i = (lt >> 5) + 16 * t;
+                float4 v = rw.g[t];
+                const float c = rw.coef[t];
+                v.x *= c, v.y *= c, v.z *= c, v.w *= c;
+                if (P.acts) {
+                    v.x *= act_grad_from_out(rw.a[t].x, P.act);
+                    v.y *= act_grad_from_out(rw.a[t].y, P.act);
+                    v.z *= act_grad_from_out(rw.a[t].z, P.act);
+                    v.w *= act_grad_from_out(rw.a[t].w, P.act);
+                }
+                bsum.x += v.x, bsum.y += v.y, bsum.z += v.z, bsum.w += v.w;
+                float4 hi, lo;
+                split_tf32(v, hi, lo);
+                const uint32_t off = swz_mn(jc, i);
+                *reinterpret_cast<float4*>(base + off) = hi;
+                *reinterpret_cast<float4*>(base + a_bytes + off) = lo;
+                const int q = lt + t * kDwLoadThreads;
+                if (q < kDwRows * kchunks) {
+                    const int ib = q / kchunks, k = (q % kchunks) * 4;
+                    split_tf32(rw.x[t], hi, lo);
+                    const uint32_t offb = swz_mn(k, ib);
+                    *reinterpret_cast<float4*>(base + 2 * a_bytes + offb) = hi;
+                    *reinterpret_cast<float4*>(base + 2 * a_bytes + b_bytes + offb) = lo;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(full + stage));
+            if (++stage == P.stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        };
+        if (0 < total) issue(0, ring[0]);
+        if (1 < total) issue(1, ring[1]);
+        for (int64_t st = 0; st < total; st += 2) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                if (st + d < total) {
+                    consume(ring[d]);
+                    if (st + d + 2 < total) issue(st + d + 2, ring[d]);
+                }
+            }
+        }
+        float* sd = s_db + (lt >> 5) * 128 + jc;
+        sd[0] = bsum.x, sd[1] = bsum.y, sd[2] = bsum.z, sd[3] = bsum.w;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kDwEpiWarps) tmem_dealloc(tmem_base, P.tmem_cols);
+    if (threadIdx.x < 128) {   // db partial: fixed-order sum over the 16 loader row lanes
+        float s = 0.f;
+        for (int t = 0; t < 16; ++t) s += s_db[t * 128 + threadIdx.x];
+        P.part[((int64_t)blockIdx.x * (2 * H) + j0 + threadIdx.x) * P.part_ld + K] = s;
+    }
+}
+
+__global__ void k_pair_dw_tc_reduce(const float* __restrict__ part, int splits, int h, int K, int part_ld,
+                                    float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
+                                    float* __restrict__ db1) {
+    const int J = 2 * h;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= (int64_t)J * (K + 1)) return;
+    const int j = (int)(e / (K + 1)), k = (int)(e % (K + 1));
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += part[((int64_t)sp * J + j) * part_ld + k];   // fixed order
+    const int jr = j < h ? j : j - h;
+    if (k < K) (j < h ? dw0 : dw1)[(int64_t)jr * K + k] = s;
+    else (j < h ? db0 : db1)[jr] = s;
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -475,6 +756,67 @@ int pair_bwd_dx_tc(const float* dout, int64_t lddo, const float* acts, const flo
     P.da1 = da1, P.ldda1 = ldda1, P.da2 = da2, P.ldda2 = ldda2;
     P.kdim = 2 * h, P.ndim = k1 + k2;
     return launch<true>(P, st);
+}
+
+
+bool pair_dw_tc_supported(int k1, int k2, int h, int64_t lda1, int64_t lda2, const void* a1, const void* a2) {
+    const int K = k1 + k2;
+    if (!(h == 64 || h == 128)) return false;                    // 2h = whole 128-row MMA tiles
+    if (!(K == 32 || K == 64 || K == 96 || K == 128)) return false;   // whole 32-element atoms, N <= 128
+    if (k1 % 4 || k2 % 4 || lda1 % 4 || !aligned16(a1)) return false;
+    if (k2 && (lda2 % 4 || !aligned16(a2))) return false;
+    return true;
+}
+
+static int64_t dw_tc_rows_per_cta(int64_t n) {
+    int64_t r = ceil_div(ceil_div(n, 148), kDwRows) * kDwRows;
+    return r < kDwRows ? kDwRows : r;
+}
+
+size_t pair_dw_tc_workspace_bytes(int64_t n, int h, int k) {
+    const int64_t splits = ceil_div(n > 0 ? n : 1, dw_tc_rows_per_cta(n));
+    return (size_t)splits * 2 * (size_t)h * ((size_t)k + 4) * sizeof(float);
+}
+
+int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const float* a1, int64_t lda1, int k1,
+                   const float* a2, int64_t lda2, int k2, const uint8_t* mask, float z, int act, float* dw0, float* db0,
+                   float* dw1, float* db1, int64_t n, int h, void* workspace, cudaStream_t st) {
+    if (lddo % 4 || !aligned16(dout) || (acts && !aligned16(acts)) || !aligned16(workspace)) {
+        set_error("pair_linear_mix_bwd dW (tcgen05): operands must be 16-byte aligned");
+        return GLASS_ERR_UNSUPPORTED;
+    }
+    const int K = k1 + k2;
+    DwParams P{};
+    P.dout = dout, P.lddo = lddo, P.acts = acts, P.mask = mask, P.z = z, P.act = act, P.h = h;
+    P.a1 = a1, P.lda1 = lda1, P.k1 = k1, P.a2 = a2, P.lda2 = lda2, P.k2 = k2, P.n = n;
+    P.part = static_cast<float*>(workspace);
+    P.part_ld = K + 4;
+    P.rows_per_cta = dw_tc_rows_per_cta(n);
+    const int splits = (int)ceil_div(n, P.rows_per_cta);
+    const size_t stage_bytes = 2 * (size_t)128 * 128 + 2 * (size_t)K * 128;
+    const size_t fixed = 1024 + 256 + 16 * 128 * sizeof(float);
+    int stages = (int)(((size_t)kMaxSmem - fixed) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 2) {
+        set_error("pair_linear_mix_bwd dW (tcgen05): shape does not fit");
+        return GLASS_ERR_UNSUPPORTED;
+    }
+    P.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)K) cols <<= 1;
+    P.tmem_cols = cols;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)splits, (unsigned)(2 * h / 128));
+    k_pair_dw_tc<<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
+    GLASS_LAUNCH_CHECK();
+    const int64_t total = 2 * (int64_t)h * (K + 1);
+    k_pair_dw_tc_reduce<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(P.part, splits, h, K, P.part_ld, dw0, db0, dw1, db1);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
 }
 
 }  // namespace glass
