@@ -426,10 +426,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
 // ---------------------------------------------------------------------------------------------
 // dW / db on tensor cores:  dWcat[2H x K] = dP^T[2H x n] * A[n x K],  db = column sums of dP.
 // The reduction runs over graph rows, so both operands are MN-major in their natural row-major global
-// layout (dP[i][j], A[i][k]: the non-reduction index is contiguous).  Each stage holds 32 rows i:
-//   operand tile = MN-atoms of 32 elements (128 B) x 8 rows (1024 B, 128B swizzle on the row index),
-//   4 row-groups per atom column (SBO = 1024), atom columns 4096 B apart (LBO = 4096)
-// (canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) of the UMMA MN-major descriptor).
+// layout (dP[i][j], A[i][k]: the non-reduction index is contiguous).  MN-major 32-bit operands must use the
+// SWIZZLE_128B_BASE32B layout: atoms of 32 elements (128 B) x 4 reduction rows (512 B) whose 32-byte chunks
+// are XOR-swizzled with the row index (Swizzle<2,5,2> on the byte address).  Each stage holds 32 rows i:
+//   8 row-groups per atom column (SBO = 512), atom columns 4096 B apart (LBO = 4096); one K = 8 MMA
+//   consumes two row-groups, i.e. advances the start address by 1024 B
+// (canonical layout ((T,8,m),(4,k)):((1,T,LBO),(8T,SBO)) of the UMMA MN-major descriptor).
 // CTA s reduces rows [s*R, (s+1)*R) into one TMEM accumulator and writes part[s]; a second kernel sums
 // the partials in CTA order (deterministic).  21 warps: 0-3 epilogue, 4 MMA, 5-20 loaders.
 // ---------------------------------------------------------------------------------------------
@@ -463,14 +465,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
     d |= (uint64_t)(4096 >> 4) << 16;               // LBO: next 32-element atom column
-    d |= (uint64_t)(1024 >> 4) << 32;               // SBO: next group of 8 reduction rows
+    d |= (uint64_t)(512 >> 4) << 32;                // SBO: next group of 4 reduction rows
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                         // SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
     return d;
 }
 // element chunk (4 consecutive MN elements starting at `mn`, reduction row `i` of the stage)
 __device__ __forceinline__ uint32_t swz_mn(int mn, int i) {
-    return (uint32_t)((mn >> 5) * 4096 + (i >> 3) * 1024 + (i & 7) * 128 + ((((mn & 31) >> 2) ^ (i & 7)) << 4));
+    const int c16 = (mn & 31) >> 2;                 // 16-byte chunk inside the 128-byte atom row
+    return (uint32_t)((mn >> 5) * 4096 + (i >> 2) * 512 + (i & 3) * 128 + ((((c16 >> 1) ^ (i & 3)) << 5) | ((c16 & 1) << 4)));
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) {
