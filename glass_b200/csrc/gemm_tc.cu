@@ -177,8 +177,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     uint64_t* tfull = bars + 2 * P.stages;     // [2]        mma -> epilogue
     uint64_t* tempty = tfull + 2;              // [2]        epilogue -> mma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [2H]: b0 | b1 (forward only), 16-byte aligned
 
     // ---- one-time setup ------------------------------------------------------------------
+    if (!BWD)
+        for (int c = threadIdx.x; c < 2 * H; c += kThreads) s_bias[c] = c < H ? P.b0[c] : P.b1[c - H];
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(smem_u32(full + s), kLoadThreads);
@@ -250,13 +253,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     float p0[8], p1[8];
                     tmem_ld8(t_row + (uint32_t)c, p0);
                     tmem_ld8(t_row + (uint32_t)(H + c), p1);
+                    const float4 ba0 = *reinterpret_cast<const float4*>(s_bias + c);
+                    const float4 ba1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+                    const float4 bb0 = *reinterpret_cast<const float4*>(s_bias + H + c);
+                    const float4 bb1 = *reinterpret_cast<const float4*>(s_bias + H + c + 4);
+                    const float bA[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
+                    const float bB[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
                     tmem_ld_wait();
                     if (row_ok) {
                         float o[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            p0[u] = act_fwd(p0[u] + __ldg(P.b0 + c + u), P.act);
-                            p1[u] = act_fwd(p1[u] + __ldg(P.b1 + c + u), P.act);
+                            p0[u] = act_fwd(p0[u] + bA[u], P.act);
+                            p1[u] = act_fwd(p1[u] + bB[u], P.act);
                             o[u] = __fadd_rn(__fmul_rn(c1, p1[u]), __fmul_rn(c0, p0[u]));
                         }
                         float4* po = reinterpret_cast<float4*>(P.out + row * P.ldo + c);
@@ -662,18 +671,30 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
     }
 }
 
-__global__ void k_pair_dw_tc_reduce(const float* __restrict__ part, int splits, int h, int K, int part_ld,
-                                    float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
-                                    float* __restrict__ db1) {
+// 256 threads = 32 output elements x 8 split lanes; lane q sums splits q, q+8, ... in order, the 8 lane
+// partials are added in lane order (deterministic).
+__global__ void __launch_bounds__(256) k_pair_dw_tc_reduce(const float* __restrict__ part, int splits, int h, int K,
+                                                           int part_ld, float* __restrict__ dw0, float* __restrict__ db0,
+                                                           float* __restrict__ dw1, float* __restrict__ db1) {
+    __shared__ float sm[8][33];
     const int J = 2 * h;
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= (int64_t)J * (K + 1)) return;
-    const int j = (int)(e / (K + 1)), k = (int)(e % (K + 1));
+    const int el = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int64_t e = blockIdx.x * 32ll + el;
+    const bool ok = e < (int64_t)J * (K + 1);
+    const int j = ok ? (int)(e / (K + 1)) : 0, k = ok ? (int)(e % (K + 1)) : 0;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += part[((int64_t)sp * J + j) * part_ld + k];   // fixed order
-    const int jr = j < h ? j : j - h;
-    if (k < K) (j < h ? dw0 : dw1)[(int64_t)jr * K + k] = s;
-    else (j < h ? db0 : db1)[jr] = s;
+    if (ok)
+        for (int sp = q; sp < splits; sp += 8) s += part[((int64_t)sp * J + j) * part_ld + k];
+    sm[q][el] = s;
+    __syncthreads();
+    if (q == 0 && ok) {
+        float t = sm[0][el];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t += sm[i][el];
+        const int jr = j < h ? j : j - h;
+        if (k < K) (j < h ? dw0 : dw1)[(int64_t)jr * K + k] = t;
+        else (j < h ? db0 : db1)[jr] = t;
+    }
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -683,7 +704,7 @@ bool plan(int kdim, int ndim, int* stages, size_t* bytes, uint32_t* tmem_cols) {
     if (ndim < 16 || ndim > 256 || ndim % 16 || kdim < 8 || kdim % 8 || kdim > 512) return false;
     const int nkb = (kdim + KBF - 1) / KBF;
     const size_t b = (size_t)2 * nkb * ndim * 128;
-    const size_t fixed = b + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    const size_t fixed = b + 1024 /*alignment slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
     if (fixed + 2 * (size_t)kStageBytes > (size_t)kMaxSmem) return false;
     int s = (int)(((size_t)kMaxSmem - fixed) / kStageBytes);
     if (s > 6) s = 6;
@@ -817,7 +838,7 @@ int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const flo
     k_pair_dw_tc<<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
     const int64_t total = 2 * (int64_t)h * (K + 1);
-    k_pair_dw_tc_reduce<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(P.part, splits, h, K, P.part_ld, dw0, db0, dw1, db1);
+    k_pair_dw_tc_reduce<<<(unsigned)ceil_div(total, 32), 256, 0, st>>>(P.part, splits, h, K, P.part_ld, dw0, db0, dw1, db1);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

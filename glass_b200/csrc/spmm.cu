@@ -10,13 +10,14 @@
 //
 // Roofline: compulsory HBM bytes = 4(N+1) + 8 nnz + 8 N H.  The gathers
 // (4 H nnz bytes) are served by L1/L2: X (14.7 MB at the em_user shape) is L2-resident.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace glass {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
 
 template <int VEC>
 struct Vec;
@@ -43,8 +44,8 @@ struct Vec<1> {
 };
 
 // G lanes per row, VEC floats per lane and chunk, KCH column chunks per lane (h <= G*VEC*KCH).
-template <int G, int VEC, int KCH>
-__global__ void __launch_bounds__(kThreads) k_spmm(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+template <int G, int VEC, int KCH, int kUnroll, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_spmm(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                    const float* __restrict__ val, const float* __restrict__ x,
                                                    int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t n_rows,
                                                    int h) {
@@ -112,14 +113,14 @@ __global__ void __launch_bounds__(kThreads) k_spmm(const int32_t* __restrict__ r
     }
 }
 
-template <int G, int VEC, int KCH>
+template <int G, int VEC, int KCH, int U = 4, int MINB = 2>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
            int64_t ldy, int64_t n_rows, int h, cudaStream_t st) {
     const int64_t groups_per_block = kThreads / G;
     int64_t blocks = ceil_div(n_rows, groups_per_block);
     const int64_t cap = (int64_t)sm_count() * 8 * 4;  // a few waves of resident CTAs; rows are interleaved
     if (blocks > cap) blocks = cap;
-    k_spmm<G, VEC, KCH><<<(unsigned)blocks, kThreads, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, h);
+    k_spmm<G, VEC, KCH, U, MINB><<<(unsigned)blocks, kThreads, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, h);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }
@@ -143,7 +144,18 @@ extern "C" int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const f
         if (lanes <= 2) GO(2, 4, 1);
         if (lanes <= 4) GO(4, 4, 1);
         if (lanes <= 8) GO(8, 4, 1);
-        if (lanes <= 16) GO(16, 4, 1);
+        if (lanes <= 16) {
+            static const int variant = getenv("GLASS_SPMM_VARIANT") ? atoi(getenv("GLASS_SPMM_VARIANT")) : 0;
+            switch (variant) {   // tuning knob: gathers in flight per lane x resident CTAs per SM
+                case 1: return launch<16, 4, 1, 8, 4>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+                case 2: return launch<16, 4, 1, 8, 3>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+                case 3: return launch<16, 4, 1, 4, 5>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+                case 4: return launch<16, 4, 1, 6, 4>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+                case 5: return launch<16, 4, 1, 2, 8>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+                case 6: return launch<16, 4, 1, 16, 2>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+                default: return launch<16, 4, 1, 4, 4>(rowptr, col, val, x, ldx, y, ldy, n_rows, h, st);
+            }
+        }
         if (lanes <= 32) GO(32, 4, 1);
         GO(32, 4, 2);
     } else {
