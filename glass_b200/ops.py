@@ -94,8 +94,8 @@ def _define(schema: str, fn):
 def _spmm_csr_(rowptr, col, val, x, y):
     lib = _lib.load()
     n_rows, h = y.shape
-    check(lib.glass_spmm_csr(_p(rowptr), _p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows, h,
-                             _stream()), "spmm_csr")
+    check(lib.glass_spmm_csr(_p(rowptr), _p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows,
+                             x.shape[0], h, _stream()), "spmm_csr")
     _count(1)
 
 

@@ -71,10 +71,10 @@ int glass_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t
 /* ------------------------------------------------------------------------------------------
  * adj @ x  (impl/models.py:164; backward = the same kernel on the transposed CSR)
  * y[r, :] = sum_{e in row r} val[e] * x[col[e], :]  accumulated in CSR order (deterministic).
- * n_rows = rows of the CSR block; x must hold every column index referenced.
+ * n_rows = rows of the CSR block; n_cols = rows of x (every column index must be < n_cols).
  * ------------------------------------------------------------------------------------------ */
 int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
-                   int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int h, void* stream);
+                   int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Label-mixed pair of Linear layers  (impl/models.py:158-162 with activation, :169-173 without)
