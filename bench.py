@@ -306,8 +306,13 @@ def run_product(args):
                                     "ms_per_step": per * 1e3}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL kernels are still alive; tearing the communicator down under them
+        # can hang, so synchronise, flush and leave without running destructors.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
