@@ -307,9 +307,9 @@ def run_product(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels are still alive; tearing the communicator down under them
-        # can hang, so synchronise, flush and leave without running destructors.
+        # can hang, so every rank synchronises its device, flushes and leaves without running destructors
+        # (no collective is pending: the last one was the e2e max-reduce above).
         torch.cuda.synchronize()
-        dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
