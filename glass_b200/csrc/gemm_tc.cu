@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
         struct Raw {
             float4 g[4];
             float4 a[BWD ? 4 : 1];
-            float coef[BWD ? 4 : 1];
-        };
+            uint32_t lab[BWD ? 4 : 1];   // raw label byte: turned into the mix coefficient only when consumed,
+        };                                 // so that issuing a stage never waits on a load
         Raw ring[D];
 
         auto issue = [&](int64_t seq, Raw& rw) {
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                 rw.g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (BWD) {
                     rw.a[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    rw.coef[i] = 0.f;
+                    rw.lab[i] = 2u;              // 2 = row / column out of range -> coefficient 0
                 }
                 if (row < P.n && k < K) {
                     if (!BWD) {
@@ -374,14 +374,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         const int br = k >= H;
                         rw.g[i] = ldg_f4(P.dout + row * P.lddo + (k - br * H));
                         if (P.acts) rw.a[i] = ldg_f4(P.acts + row * (2 * (int64_t)H) + k);
-                        rw.coef[i] = ((P.mask[row] != 0) == (br != 0)) ? P.z : 1.f - P.z;
+                        rw.lab[i] = P.mask[row];
                     }
                 }
             }
         };
         int stage = 0;
         uint32_t phase = 0;
-        auto consume = [&](const Raw& rw) {
+        auto consume = [&](const Raw& rw, int kb_of_slot) {
+            (void)kb_of_slot;
             mbar_wait(smem_u32(empty + stage), phase ^ 1);
             uint8_t* dst = a_ring + (size_t)stage * kStageBytes;
 #pragma unroll
@@ -390,7 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                 const uint32_t off = swz(q >> 3, q & 7);
                 float4 v = rw.g[i];
                 if (BWD) {
-                    const float c = rw.coef[i];
+                    // chunk q & 7 of this K-block covers pre-activation columns of ONE branch (H % 4 == 0)
+                    const int br = (kb_of_slot * KBF + (q & 7) * 4) >= H;
+                    const float c = rw.lab[i] > 1u ? 0.f : (((rw.lab[i] != 0) == (br != 0)) ? P.z : 1.f - P.z);
                     v.x *= c, v.y *= c, v.z *= c, v.w *= c;
                     if (P.acts) {
                         v.x *= act_grad_from_out(rw.a[i].x, P.act);
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 if (seq + d < total) {
-                    consume(ring[d]);
+                    consume(ring[d], (int)((seq + d) % nkb));
                     if (seq + d + D < total) issue(seq + d + D, ring[d]);
                 }
             }
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
         float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
         struct Raw {
             float4 g[2], a[2], x[2];
-            float coef[2];
+            uint32_t lab[2];             // raw label byte (2 = row out of range); coefficient derived when consumed
         };
         Raw ring[2];
         auto issue = [&](int64_t st, Raw& rw) {
@@ -591,11 +594,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
                 const int64_t row = r0 + i;
                 rw.g[t] = make_float4(0.f, 0.f, 0.f, 0.f);
                 rw.a[t] = make_float4(1.f, 1.f, 1.f, 1.f);
-                rw.coef[t] = 0.f;
+                rw.lab[t] = 2u;
                 if (row < m_hi) {
                     rw.g[t] = ldg_f4(P.dout + row * P.lddo + (j - br * H));
                     if (P.acts) rw.a[t] = ldg_f4(P.acts + row * (2 * (int64_t)H) + j);
-                    rw.coef[t] = ((P.mask[row] != 0) == (br != 0)) ? P.z : 1.f - P.z;
+                    rw.lab[t] = P.mask[row];
                 }
                 const int q = lt + t * kDwLoadThreads;
                 rw.x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
             for (int t = 0; t < 2; ++t) {
                 const int i = (lt >> 5) + 16 * t;
                 float4 v = rw.g[t];
-                const float c = rw.coef[t];
+                const float c = rw.lab[t] > 1u ? 0.f : (((rw.lab[t] != 0) == (br != 0)) ? P.z : 1.f - P.z);
                 v.x *= c, v.y *= c, v.z *= c, v.w *= c;
                 if (P.acts) {
                     v.x *= act_grad_from_out(rw.a[t].x, P.act);
