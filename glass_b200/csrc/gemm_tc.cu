@@ -9,11 +9,11 @@
 // far inside the 1e-4 bar (the dropped Alo*Blo term is ~2^-22).  K <= 256, so the GEMM is HBM-bound even at
 // 3x the MMA count.
 //
-// CTA = 17 warps, persistent over 128-row tiles (grid = #SMs):
+// CTA = 25 warps, persistent over 128-row tiles (grid = #SMs):
 //   warps 0-7  epilogue: tcgen05.ld (TMEM lane = row; warp w reads lane quadrant w % 4, warps w and w+4
 //              split the columns) -> bias/act/mix -> global
 //   warp  8    TMEM allocator; lane 0 issues tcgen05.mma / tcgen05.commit
-//   warps 9-16 operand loader: coalesced float4 global loads kept in a register ring 2-3 K-blocks deep
+//   warps 9-24 operand loader: coalesced float4 global loads kept in a register ring 3-4 K-blocks deep
 //              -> hi/lo split -> st.shared into the 128B-swizzled K-major UMMA layout ->
 //              fence.proxy.async -> mbarrier arrive
 // The weight operand (both weight sets, hi and lo) stays resident in shared memory for the CTA's lifetime;
@@ -26,9 +26,10 @@ namespace {
 
 constexpr int BM = 128;                 // rows per tile == UMMA M (TMEM lane == row)
 constexpr int KBF = 32;                 // floats per K-block == one 128-byte swizzle row
-constexpr int kEpiWarps = 8, kLoadWarps = 8;
+constexpr int kEpiWarps = 8, kLoadWarps = 16;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;
+constexpr int kCPT = BM * 8 / kLoadThreads;   // 16-byte chunks per loader thread and K-block
 constexpr int kStageBytes = BM * 128 * 2;   // hi + lo tile of one K-block
 constexpr int kMaxSmem = 232448;            // 227 KB opt-in limit per CTA
 
@@ -341,22 +342,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
         }
     } else {
         // ================================ operand loader ====================================
-        const int lt = threadIdx.x - (kEpiWarps + 1) * 32;                 // 0 .. 255
+        const int lt = threadIdx.x - (kEpiWarps + 1) * 32;                 // 0 .. kLoadThreads-1
         const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t total = my_tiles * nkb;                              // K-blocks this CTA streams
-        constexpr int D = BWD ? 2 : 3;                                     // register ring depth (K-blocks in flight)
+        constexpr int D = BWD ? 2 : 4;                                     // register ring depth (K-blocks in flight)
         struct Raw {
-            float4 g[4];
-            float4 a[BWD ? 4 : 1];
-            uint32_t lab[BWD ? 4 : 1];   // raw label byte: turned into the mix coefficient only when consumed,
-        };                                 // so that issuing a stage never waits on a load
+            float4 g[kCPT];
+            float4 a[BWD ? kCPT : 1];
+            uint32_t lab[BWD ? kCPT : 1];   // raw label byte: turned into the mix coefficient only when consumed,
+        };                                    // so that issuing a stage never waits on a load
         Raw ring[D];
 
         auto issue = [&](int64_t seq, Raw& rw) {
             const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
             const int kb = (int)(seq % nkb);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kCPT; ++i) {
                 const int q = lt + i * kLoadThreads;
                 const int r = q >> 3, ch = q & 7;
                 const int64_t row = tile * BM + r;
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             mbar_wait(smem_u32(empty + stage), phase ^ 1);
             uint8_t* dst = a_ring + (size_t)stage * kStageBytes;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kCPT; ++i) {
                 const int q = lt + i * kLoadThreads;
                 const uint32_t off = swz(q >> 3, q & 7);
                 float4 v = rw.g[i];
@@ -448,7 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
 // the partials in CTA order (deterministic).  21 warps: 0-3 epilogue, 4 MMA, 5-20 loaders.
 // ---------------------------------------------------------------------------------------------
 constexpr int kDwLoadWarps = 16, kDwLoadThreads = kDwLoadWarps * 32, kDwEpiWarps = 4;
-constexpr int kDwThreads = (kDwEpiWarps + 1 + kDwLoadWarps) * 32;
+constexpr int kDwThreads = (kDwLoadWarps + 1) * 32;
+constexpr int kDwMmaWarp = kDwLoadWarps;
 constexpr int kDwRows = 32;                    // reduction rows per stage
 
 struct DwParams {
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
         mbar_init(smem_u32(tfull), 1);
         fence_barrier_init();
     }
-    if (warp == kDwEpiWarps) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    if (warp == kDwMmaWarp) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -522,29 +524,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
     const int64_t m_hi = min(m_lo + P.rows_per_cta, P.n);
     const int64_t total = m_hi > m_lo ? (m_hi - m_lo + kDwRows - 1) / kDwRows : 0;   // stages to stream
 
-    if (warp < kDwEpiWarps) {
-        // -------- epilogue (after the whole reduction) --------
-        if (total > 0) {
-            mbar_wait(smem_u32(tfull), 0);
-            tc_fence_after();
-        }
-        const int j = warp * 32 + lane;
-        float* dst = P.part + ((int64_t)blockIdx.x * (2 * H) + j0 + j) * P.part_ld;
-        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c = 0; c < K; c += 8) {
-            float d[8];
-            if (total > 0) {
-                tmem_ld8(t_row + (uint32_t)c, d);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) d[u] = 0.f;
-            }
-            reinterpret_cast<float4*>(dst + c)[0] = make_float4(d[0], d[1], d[2], d[3]);
-            reinterpret_cast<float4*>(dst + c)[1] = make_float4(d[4], d[5], d[6], d[7]);
-        }
-        tc_fence_before();
-    } else if (warp == kDwEpiWarps) {
+    if (warp == kDwMmaWarp) {
         // -------- MMA issuer --------
         if (lane == 0 && total > 0) {
             const uint32_t idesc = make_idesc(128, K) | (1u << 15) | (1u << 16);   // both operands MN-major
@@ -575,7 +555,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
         }
     } else {
         // -------- loaders: straight row-major copies into the MN-major tiles --------
-        const int lt = threadIdx.x - (kDwEpiWarps + 1) * 32;        // 0 .. 511
+        const int lt = threadIdx.x;                                  // 0 .. 511
         const int jc = (lt & 31) * 4;                                // this thread's 4 dP columns (fixed)
         const int j = j0 + jc;
         const int br = j >= H;
@@ -661,12 +641,35 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
         }
         float* sd = s_db + (lt >> 5) * 128 + jc;
         sd[0] = bsum.x, sd[1] = bsum.y, sd[2] = bsum.z, sd[3] = bsum.w;
+        if (warp < kDwEpiWarps) {
+        // -------- epilogue (after the whole reduction): loader warps 0-3 own TMEM lane quadrants 0-3 --------
+        if (total > 0) {
+            mbar_wait(smem_u32(tfull), 0);
+            tc_fence_after();
+        }
+        const int j = warp * 32 + lane;
+        float* dst = P.part + ((int64_t)blockIdx.x * (2 * H) + j0 + j) * P.part_ld;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < K; c += 8) {
+            float d[8];
+            if (total > 0) {
+                tmem_ld8(t_row + (uint32_t)c, d);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d[u] = 0.f;
+            }
+            reinterpret_cast<float4*>(dst + c)[0] = make_float4(d[0], d[1], d[2], d[3]);
+            reinterpret_cast<float4*>(dst + c)[1] = make_float4(d[4], d[5], d[6], d[7]);
+        }
+        tc_fence_before();
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == kDwEpiWarps) tmem_dealloc(tmem_base, P.tmem_cols);
+    if (warp == kDwMmaWarp) tmem_dealloc(tmem_base, P.tmem_cols);
     if (threadIdx.x < 128) {   // db partial: fixed-order sum over the 16 loader row lanes
         float s = 0.f;
         for (int t = 0; t < 16; ++t) s += s_db[t * 128 + threadIdx.x];
