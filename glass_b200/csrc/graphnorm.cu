@@ -4,8 +4,8 @@
 //   mu = mean_rows(x); o = x - mean_scale*mu; var = mean_rows(o^2) = E[x^2] - (2a - a^2) mu^2
 //   out = keep * pscale * act(weight * o / sqrt(var + eps) + bias)
 //
-// Forward = column sums of x and x^2 (fp64 accumulators, per-CTA partials reduced in CTA order, so the
-// result is run-to-run deterministic) -> per-column constants -> one elementwise pass.
+// Forward = column sums of x and x^2 (fp64 accumulators, per-CTA partials reduced in CTA order by the last
+// CTA to finish, so the result is run-to-run deterministic) -> per-column constants -> one elementwise pass.
 // Backward = column sums S1 = sum u, S2 = sum u*yhat with u = dout*keep*pscale*act'(pre)
 //   dweight = S2, dbias = S1, sum_do = rstd*w*(S1 - sum(yhat)*S2/N), dmean_scale = -mu*sum_do
 //   dx = rstd*w*u - (rstd*w*S2/N)*yhat - mean_scale*sum_do/N                 (one elementwise pass)
@@ -22,11 +22,70 @@ constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs; fixed so the 
 // stats rows
 enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4 };
 
+// Finalisation runs in the LAST CTA to finish k_colsums (ticket counter), so a GraphNorm pass is two
+// launches (statistics, apply) instead of three.  One warp per column: lane l adds partials l, l+32, ...
+// in order, then a fixed butterfly -> deterministic.
+struct Fin {
+    const float* weight;
+    const float* bias;        // fwd only
+    const float* mean_scale;
+    float eps;                // fwd only
+    float* stats;             // fwd: written; bwd: read
+    float* coef;              // bwd
+    float* dweight;
+    float* dbias;
+    float* dmean_scale;
+    unsigned int* counter;    // zero on entry, left zero on exit
+};
+
+__device__ __forceinline__ void reduce_partials(const double* partial, int nblk, int c, int col, double& s, double& q) {
+    const int lane = threadIdx.x & 31;
+    s = 0.0;
+    q = 0.0;
+    for (int b = lane; b < nblk; b += 32) {
+        s += __ldcg(partial + ((int64_t)b * 2 + 0) * c + col);
+        q += __ldcg(partial + ((int64_t)b * 2 + 1) * c + col);
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+}
+
+__device__ __forceinline__ void finalize_fwd_col(const Fin& f, double s, double q, int64_t n, int c, int col) {
+    const double mu = s / (double)n, ex2 = q / (double)n;
+    const float muf = (float)mu;
+    const float am = __fmul_rn(muf, f.mean_scale[col]);  // mean * mean_scale, rounded like the reference
+    // var of (x - am): E[x^2] - 2*am*mu + am^2, evaluated in fp64
+    double var = ex2 - 2.0 * (double)am * mu + (double)am * (double)am;
+    if (var < 0.0) var = 0.0;
+    const float std_ = sqrtf((float)var + f.eps);
+    const float rstd = 1.0f / std_;
+    f.stats[ST_SCALE * c + col] = f.weight[col] * rstd;
+    f.stats[ST_AM * c + col] = am;
+    f.stats[ST_MU * c + col] = muf;
+    f.stats[ST_RSTD * c + col] = rstd;
+    f.stats[ST_BIAS * c + col] = f.bias[col];  // kept with the statistics so that backward can rebuild the pre-activation
+}
+
+// coef rows: alpha, beta, gamma
+__device__ __forceinline__ void finalize_bwd_col(const Fin& f, double s1, double s2, int64_t n, int c, int col) {
+    const double w = f.weight[col], a = f.mean_scale[col];
+    const double rstd = f.stats[ST_RSTD * c + col], mu = f.stats[ST_MU * c + col], am = f.stats[ST_AM * c + col];
+    const double N = (double)n;
+    const double sum_yhat = rstd * N * (mu - am);
+    const double sum_do = rstd * w * (s1 - sum_yhat * s2 / N);
+    f.dweight[col] = (float)s2;
+    f.dbias[col] = (float)s1;
+    f.dmean_scale[col] = (float)(-mu * sum_do);
+    f.coef[0 * c + col] = (float)(rstd * w);
+    f.coef[1 * c + col] = (float)(-rstd * w * s2 / N);
+    f.coef[2 * c + col] = (float)(-a * sum_do / N);
+}
+
 template <int VEC, bool BWD>
 __global__ void __launch_bounds__(kThreads)
 k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dout, int64_t lddo,
           const float* __restrict__ stats, const float* __restrict__ bias, int act, const uint8_t* __restrict__ keep,
-          float pscale, int64_t n, int c, double* __restrict__ partial) {
+          float pscale, int64_t n, int c, double* partial, const Fin fin) {
     // thread -> (column vector cvl, row lane rl).  CVB column vectors are processed per pass.
     const int CV = (c + VEC - 1) / VEC;
     const int CVB = CV < kThreads ? CV : kThreads;
@@ -52,6 +111,7 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
                     bs[k] = bias[cc];
                 }
             }
+#pragma unroll 4
             for (int64_t r = (int64_t)blockIdx.x * nrl + rl; r < n; r += (int64_t)gridDim.x * nrl) {
                 float xv[VEC], gv[VEC];
                 if (VEC == 4) {
@@ -103,43 +163,23 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
         }
         __syncthreads();
     }
-}
-
-// One warp per column: lane l adds partials l, l+32, ... in order, then a fixed butterfly -> deterministic.
-__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int nblk, int c, int col,
-                                                double& s, double& q) {
-    const int lane = threadIdx.x & 31;
-    s = 0.0;
-    q = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
-        s += partial[((int64_t)b * 2 + 0) * c + col];
-        q += partial[((int64_t)b * 2 + 1) * c + col];
+    // last CTA to arrive reduces the partials of all CTAs in CTA order and writes the per-column constants
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int col = threadIdx.x >> 5; col < c; col += kThreads / 32) {
+        double a, b;
+        reduce_partials(partial, (int)gridDim.x, c, col, a, b);
+        if ((threadIdx.x & 31) == 0) {
+            if (BWD) finalize_bwd_col(fin, a, b, n, c, col);
+            else finalize_fwd_col(fin, a, b, n, c, col);
+        }
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-}
-
-__global__ void k_gn_finalize_fwd(const double* __restrict__ partial, int nblk, int64_t n, int c,
-                                  const float* __restrict__ weight, const float* __restrict__ bias,
-                                  const float* __restrict__ mean_scale, float eps, float* __restrict__ stats) {
-    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (col >= c) return;
-    double s, q;
-    reduce_partials(partial, nblk, c, col, s, q);
-    if ((threadIdx.x & 31) != 0) return;
-    const double mu = s / (double)n, ex2 = q / (double)n;
-    const float muf = (float)mu;
-    const float am = __fmul_rn(muf, mean_scale[col]);  // mean * mean_scale, rounded like the reference
-    // var of (x - am): E[x^2] - 2*am*mu + am^2, evaluated in fp64
-    double var = ex2 - 2.0 * (double)am * mu + (double)am * (double)am;
-    if (var < 0.0) var = 0.0;
-    const float std_ = sqrtf((float)var + eps);
-    const float rstd = 1.0f / std_;
-    stats[ST_SCALE * c + col] = weight[col] * rstd;
-    stats[ST_AM * c + col] = am;
-    stats[ST_MU * c + col] = muf;
-    stats[ST_RSTD * c + col] = rstd;
-    stats[ST_BIAS * c + col] = bias[col];  // kept with the statistics so that backward can rebuild the pre-activation
+    if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
 template <int VEC>
@@ -169,29 +209,6 @@ k_gn_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ s
         if (VEC == 4) *reinterpret_cast<float4*>(out + r * ldo + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
         else out[r * ldo + col] = ov[0];
     }
-}
-
-// coef rows: alpha, beta, gamma
-__global__ void k_gn_finalize_bwd(const double* __restrict__ partial, int nblk, int64_t n, int c,
-                                  const float* __restrict__ weight, const float* __restrict__ mean_scale,
-                                  const float* __restrict__ stats, float* __restrict__ coef, float* __restrict__ dweight,
-                                  float* __restrict__ dbias, float* __restrict__ dmean_scale) {
-    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (col >= c) return;
-    double s1, s2;
-    reduce_partials(partial, nblk, c, col, s1, s2);
-    if ((threadIdx.x & 31) != 0) return;
-    const double w = weight[col], a = mean_scale[col];
-    const double rstd = stats[ST_RSTD * c + col], mu = stats[ST_MU * c + col], am = stats[ST_AM * c + col];
-    const double N = (double)n;
-    const double sum_yhat = rstd * N * (mu - am);
-    const double sum_do = rstd * w * (s1 - sum_yhat * s2 / N);
-    dweight[col] = (float)s2;
-    dbias[col] = (float)s1;
-    dmean_scale[col] = (float)(-mu * sum_do);
-    coef[0 * c + col] = (float)(rstd * w);
-    coef[1 * c + col] = (float)(-rstd * w * s2 / N);
-    coef[2 * c + col] = (float)(-a * sum_do / N);
 }
 
 template <int VEC>
@@ -259,8 +276,8 @@ extern "C" size_t glass_graphnorm_workspace_bytes(int64_t n, int c) {
 extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                                    const float* mean_scale, float eps, int act, const uint8_t* keep, float pscale,
                                    float* out, int64_t ldo, float* stats, int64_t n, int c, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-    GLASS_CHECK_ARG(x && weight && bias && mean_scale && out && stats && n > 0 && c > 0 && ldx >= c && ldo >= c,
+                                   size_t workspace_bytes, unsigned int* counter, void* stream) {
+    GLASS_CHECK_ARG(x && weight && bias && mean_scale && out && stats && counter && n > 0 && c > 0 && ldx >= c && ldo >= c,
                     "graphnorm_fwd: bad arguments");
     if (workspace_bytes < glass_graphnorm_workspace_bytes(n, c) || !workspace) {
         set_error("graphnorm_fwd: workspace too small");
@@ -270,9 +287,10 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
     double* partial = static_cast<double*>(workspace);
     const bool vec = vec_ok(c, {ldx, ldo}, {x, out});
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
-    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
-    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
-    k_gn_finalize_fwd<<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, weight, bias, mean_scale, eps, stats);
+    Fin fin{};
+    fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats, fin.counter = counter;
+    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial, fin);
+    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial, fin);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
     if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, keep, pscale, out, ldo, n, c);
@@ -285,8 +303,8 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
                                    const float* mean_scale, const float* stats, int act, const uint8_t* keep,
                                    float pscale, float* dx, int64_t lddx, float* dweight, float* dbias,
                                    float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
-    GLASS_CHECK_ARG(dout && x && weight && mean_scale && stats && dx && dweight && dbias && dmean_scale && n > 0 &&
+                                   unsigned int* counter, void* stream) {
+    GLASS_CHECK_ARG(dout && x && weight && mean_scale && stats && dx && dweight && dbias && dmean_scale && counter && n > 0 &&
                         c > 0 && ldx >= c && lddo >= c && lddx >= c,
                     "graphnorm_bwd: bad arguments");
     if (workspace_bytes < glass_graphnorm_workspace_bytes(n, c) || !workspace) {
@@ -300,10 +318,11 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
     const float* bias = stats + ST_BIAS * (int64_t)c;  // forward bias saved with the statistics
     const bool vec = vec_ok(c, {ldx, lddo, lddx}, {x, dout, dx});
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
-    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
-    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
-    k_gn_finalize_bwd<<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, weight, mean_scale, stats, coef,
-                                                               dweight, dbias, dmean_scale);
+    Fin fin{};
+    fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
+    fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale, fin.counter = counter;
+    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial, fin);
+    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial, fin);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
     if (vec) k_gn_bwd_apply<4><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, keep, pscale, dx, lddx, n, c);

@@ -162,6 +162,19 @@ class EmbZGConv(nn.Module):
             for gn in self.gns:
                 gn.reset_parameters()
 
+    def _identity_lookup(self, ids: torch.Tensor) -> bool:
+        """--use_nodeid: ids == arange(N) and the table has N rows, so the lookup (impl/models.py:248) is the
+        identity.  Checked once per id tensor (one host sync), then cached."""
+        table = self.input_emb.weight
+        if ids.numel() != table.shape[0]:
+            return False
+        key = (ids.data_ptr(), ids._version, ids.numel(), str(ids.device))
+        hit = getattr(self, "_id_cache", None)
+        if hit is None or hit[0] != key:
+            same = bool(torch.equal(ids, torch.arange(ids.numel(), device=ids.device, dtype=ids.dtype)))
+            self._id_cache = hit = (key, same)
+        return hit[1]
+
     def forward(self, x, edge_index, edge_weight, z=None):
         if self.gns is None:
             raise NotImplementedError("gn=False is outside the accelerated GLASS path (GLASSTest.py:150 uses gn=True)")
@@ -171,7 +184,11 @@ class EmbZGConv(nn.Module):
         else:
             mask = ops.label_mask(z)                                                        # :246
         act = _act_id(self.activation)
-        h = ops.embedding(x.reshape(-1), self.input_emb.weight).reshape(n, -1)              # :248
+        ids = x.reshape(-1)
+        if ids.numel() == n and self._identity_lookup(ids):
+            h = self.input_emb.weight                                                       # :248, identity gather
+        else:
+            h = ops.embedding(ids, self.input_emb.weight).reshape(n, -1)                    # :248
         h = self.emb_gn(h, p=self.dropout, training=self.training)                          # :249-251
         xs = []
         for layer, conv in enumerate(self.convs[:-1]):                                      # :253-259
