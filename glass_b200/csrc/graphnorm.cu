@@ -4,8 +4,8 @@
 //   mu = mean_rows(x); o = x - mean_scale*mu; var = mean_rows(o^2) = E[x^2] - (2a - a^2) mu^2
 //   out = keep * pscale * act(weight * o / sqrt(var + eps) + bias)
 //
-// Forward = column sums of x and x^2 (fp64 accumulators, per-CTA partials reduced in CTA order by the last
-// CTA to finish, so the result is run-to-run deterministic) -> per-column constants -> one elementwise pass.
+// Forward = column sums of x and x^2 (fp64 accumulators, per-CTA partials reduced in CTA order, so the
+// result is run-to-run deterministic) -> per-column constants -> one elementwise pass.
 // Backward = column sums S1 = sum u, S2 = sum u*yhat with u = dout*keep*pscale*act'(pre)
 //   dweight = S2, dbias = S1, sum_do = rstd*w*(S1 - sum(yhat)*S2/N), dmean_scale = -mu*sum_do
 //   dx = rstd*w*u - (rstd*w*S2/N)*yhat - mean_scale*sum_do/N                 (one elementwise pass)
@@ -22,9 +22,9 @@ constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs; fixed so the 
 // stats rows
 enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4 };
 
-// Finalisation runs in the LAST CTA to finish k_colsums (ticket counter), so a GraphNorm pass is two
-// launches (statistics, apply) instead of three.  One warp per column: lane l adds partials l, l+32, ...
-// in order, then a fixed butterfly -> deterministic.
+// Finalisation: one warp per column; lane l adds partials l, l+32, ... in order (all loads issued up
+// front), then a fixed butterfly -> deterministic.  (A "last CTA finalises" variant was measured slower:
+// one SM pulling all 296 x 2C partials is latency bound.)
 struct Fin {
     const float* weight;
     const float* bias;        // fwd only
@@ -35,16 +35,23 @@ struct Fin {
     float* dweight;
     float* dbias;
     float* dmean_scale;
-    unsigned int* counter;    // zero on entry, left zero on exit
 };
 
 __device__ __forceinline__ void reduce_partials(const double* partial, int nblk, int c, int col, double& s, double& q) {
     const int lane = threadIdx.x & 31;
+    double vs[(kMaxPartialCtas + 31) / 32], vq[(kMaxPartialCtas + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (kMaxPartialCtas + 31) / 32; ++i) {
+        const int b = lane + 32 * i;
+        vs[i] = b < nblk ? __ldcg(partial + ((int64_t)b * 2 + 0) * c + col) : 0.0;
+        vq[i] = b < nblk ? __ldcg(partial + ((int64_t)b * 2 + 1) * c + col) : 0.0;
+    }
     s = 0.0;
     q = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
-        s += __ldcg(partial + ((int64_t)b * 2 + 0) * c + col);
-        q += __ldcg(partial + ((int64_t)b * 2 + 1) * c + col);
+#pragma unroll
+    for (int i = 0; i < (kMaxPartialCtas + 31) / 32; ++i) {
+        s += vs[i];
+        q += vq[i];
     }
     s = warp_sum(s);
     q = warp_sum(q);
@@ -85,7 +92,7 @@ template <int VEC, bool BWD>
 __global__ void __launch_bounds__(kThreads)
 k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dout, int64_t lddo,
           const float* __restrict__ stats, const float* __restrict__ bias, int act, const uint8_t* __restrict__ keep,
-          float pscale, int64_t n, int c, double* partial, const Fin fin) {
+          float pscale, int64_t n, int c, double* __restrict__ partial) {
     // thread -> (column vector cvl, row lane rl).  CVB column vectors are processed per pass.
     const int CV = (c + VEC - 1) / VEC;
     const int CVB = CV < kThreads ? CV : kThreads;
@@ -163,23 +170,17 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
         }
         __syncthreads();
     }
-    // last CTA to arrive reduces the partials of all CTAs in CTA order and writes the per-column constants
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int col = threadIdx.x >> 5; col < c; col += kThreads / 32) {
-        double a, b;
-        reduce_partials(partial, (int)gridDim.x, c, col, a, b);
-        if ((threadIdx.x & 31) == 0) {
-            if (BWD) finalize_bwd_col(fin, a, b, n, c, col);
-            else finalize_fwd_col(fin, a, b, n, c, col);
-        }
-    }
-    if (threadIdx.x == 0) *fin.counter = 0u;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) k_gn_finalize(const double* partial, int nblk, int64_t n, int c, const Fin fin) {
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= c) return;
+    double a, b;
+    reduce_partials(partial, nblk, c, col, a, b);
+    if ((threadIdx.x & 31) != 0) return;
+    if (BWD) finalize_bwd_col(fin, a, b, n, c, col);
+    else finalize_fwd_col(fin, a, b, n, c, col);
 }
 
 template <int VEC>
@@ -276,8 +277,8 @@ extern "C" size_t glass_graphnorm_workspace_bytes(int64_t n, int c) {
 extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                                    const float* mean_scale, float eps, int act, const uint8_t* keep, float pscale,
                                    float* out, int64_t ldo, float* stats, int64_t n, int c, void* workspace,
-                                   size_t workspace_bytes, unsigned int* counter, void* stream) {
-    GLASS_CHECK_ARG(x && weight && bias && mean_scale && out && stats && counter && n > 0 && c > 0 && ldx >= c && ldo >= c,
+                                   size_t workspace_bytes, void* stream) {
+    GLASS_CHECK_ARG(x && weight && bias && mean_scale && out && stats && n > 0 && c > 0 && ldx >= c && ldo >= c,
                     "graphnorm_fwd: bad arguments");
     if (workspace_bytes < glass_graphnorm_workspace_bytes(n, c) || !workspace) {
         set_error("graphnorm_fwd: workspace too small");
@@ -288,9 +289,10 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
     const bool vec = vec_ok(c, {ldx, ldo}, {x, out});
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     Fin fin{};
-    fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats, fin.counter = counter;
-    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial, fin);
-    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial, fin);
+    fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats;
+    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
+    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
+    k_gn_finalize<false><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
     if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, keep, pscale, out, ldo, n, c);
@@ -303,8 +305,8 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
                                    const float* mean_scale, const float* stats, int act, const uint8_t* keep,
                                    float pscale, float* dx, int64_t lddx, float* dweight, float* dbias,
                                    float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
-                                   unsigned int* counter, void* stream) {
-    GLASS_CHECK_ARG(dout && x && weight && mean_scale && stats && dx && dweight && dbias && dmean_scale && counter && n > 0 &&
+                                   void* stream) {
+    GLASS_CHECK_ARG(dout && x && weight && mean_scale && stats && dx && dweight && dbias && dmean_scale && n > 0 &&
                         c > 0 && ldx >= c && lddo >= c && lddx >= c,
                     "graphnorm_bwd: bad arguments");
     if (workspace_bytes < glass_graphnorm_workspace_bytes(n, c) || !workspace) {
@@ -320,9 +322,10 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     Fin fin{};
     fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
-    fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale, fin.counter = counter;
-    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial, fin);
-    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial, fin);
+    fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale;
+    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
+    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
+    k_gn_finalize<true><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
     if (vec) k_gn_bwd_apply<4><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, keep, pscale, dx, lddx, n, c);

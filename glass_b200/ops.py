@@ -135,24 +135,13 @@ _define("pair_linear_mix_bwd_(Tensor dout, Tensor? acts, Tensor a1, Tensor? a2, 
         "Tensor(e!) dw1, Tensor(f!) db1, Tensor(g!) workspace) -> ()", _pair_bwd_)
 
 
-_gn_counters = {}
-
-
-def _gn_counter(device) -> torch.Tensor:
-    """One zero-initialised uint32 ticket counter per device (the statistics kernel leaves it zero)."""
-    t = _gn_counters.get(device)
-    if t is None:
-        t = _gn_counters[device] = torch.zeros(1, dtype=torch.int32, device=device)
-    return t
-
-
 def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, pscale, out, stats, workspace):
     lib = _lib.load()
     n, c = x.shape
     check(lib.glass_graphnorm_fwd(_p(x), x.stride(0), _p(weight), _p(bias), _p(mean_scale), eps, act, _p(keep),
                                   pscale, _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
-                                  workspace.numel(), _p(_gn_counter(x.device)), _stream()), "graphnorm_fwd")
-    _count(2)
+                                  workspace.numel(), _stream()), "graphnorm_fwd")
+    _count(3)
 
 
 _define("graphnorm_fwd_(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, int act, Tensor? keep, "
@@ -164,10 +153,9 @@ def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, pscale, dx, dweight,
     n, c = x.shape
     check(lib.glass_graphnorm_bwd(_p(dout), dout.stride(0), _p(x), x.stride(0), _p(weight), _p(mean_scale),
                                   _p(stats), act, _p(keep), pscale, _p(dx), dx.stride(0), _p(dweight), _p(dbias),
-                                  _p(dmean_scale), n, c, _p(workspace), workspace.numel(),
-                                  _p(_gn_counter(x.device)), _stream()),
+                                  _p(dmean_scale), n, c, _p(workspace), workspace.numel(), _stream()),
           "graphnorm_bwd")
-    _count(2)
+    _count(3)
 
 
 _define("graphnorm_bwd_(Tensor dout, Tensor x, Tensor weight, Tensor mean_scale, Tensor stats, int act, Tensor? keep, "

@@ -110,22 +110,20 @@ int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts
  *   out = keep * pscale * act(weight*o*rstd + bias)
  * stats [5, c]: rows = scale (weight*rstd), am (mean_scale*mu), mu, rstd, bias -- written by fwd,
  * consumed by bwd.  keep: uint8 [n,c] (ld c) or NULL; pscale = 1/(1-p).
- * Column sums are accumulated in fp64 per block and reduced in block order (deterministic) by the
- * last block to finish.  workspace: glass_graphnorm_workspace_bytes(n, c).  counter: one uint32 in
- * device memory that is ZERO on entry (it is left zero on exit; calls sharing a counter must be
- * ordered on one stream).
+ * Column sums are accumulated in fp64 per block and reduced in block order (deterministic).
+ * workspace: glass_graphnorm_workspace_bytes(n, c).
  * ------------------------------------------------------------------------------------------ */
 size_t glass_graphnorm_workspace_bytes(int64_t n, int c);
 int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                         const float* mean_scale, float eps, int act, const uint8_t* keep, float pscale,
                         float* out, int64_t ldo, float* stats, int64_t n, int c, void* workspace,
-                        size_t workspace_bytes, unsigned int* counter, void* stream);
+                        size_t workspace_bytes, void* stream);
 /* dx [n,c]; dweight, dbias, dmean_scale [c] are OVERWRITTEN (not accumulated). */
 int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* weight,
                         const float* mean_scale, const float* stats, int act, const uint8_t* keep,
                         float pscale, float* dx, int64_t lddx, float* dweight, float* dbias,
                         float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
-                        unsigned int* counter, void* stream);
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * nn.Embedding lookup (impl/models.py:248) and its dense gradient.
