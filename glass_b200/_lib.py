@@ -28,6 +28,11 @@ PROTOTYPES = {
     "glass_csr_build": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                C.POINTER(C.c_int64), _vp, _sz, _vp]),
     "glass_spmm_csr": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
+    "glass_spmm_plan_size": (_i32, [_vp, _i64, _i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int64), _vp]),
+    "glass_spmm_plan_build": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "glass_spmm_csr_planned": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i64,
+                                      _vp, _vp, _vp, _i64, _vp, _vp]),
     "glass_pair_linear_mix_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
                                          _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "glass_pair_linear_mix_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),

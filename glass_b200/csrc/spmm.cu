@@ -12,6 +12,9 @@
 // (4 H nnz bytes) are served by L1/L2: X (14.7 MB at the em_user shape) is L2-resident.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace glass {
@@ -43,13 +46,41 @@ struct Vec<1> {
     static __device__ __forceinline__ void fma(T& a, float s, const T& x) { a = fmaf(s, x, a); }
 };
 
+// Work description: either one item per CSR row, or a precomputed plan in which rows longer than
+// `max_len` entries are split into several items whose partial sums go to a scratch matrix
+// (skewed / power-law graphs: a hub row would otherwise serialise on one lane group).
+struct RowWork {
+    const int32_t* rowptr;
+    float* y;
+    int64_t ldy;
+    __device__ __forceinline__ void get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
+        b = __ldg(rowptr + item);
+        e = __ldg(rowptr + item + 1);
+        dst = y + item * ldy;
+    }
+};
+struct PlanWork {
+    const int32_t* item_begin;
+    const int32_t* item_end;
+    const int32_t* item_dst;   // >= 0: row of y; < 0: scratch row (-1 - dst)
+    float* y;
+    int64_t ldy;
+    float* scratch;            // [n_slots, ld_s]
+    int64_t ld_s;
+    __device__ __forceinline__ void get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
+        b = __ldg(item_begin + item);
+        e = __ldg(item_end + item);
+        const int32_t d = __ldg(item_dst + item);
+        dst = d >= 0 ? y + (int64_t)d * ldy : scratch + (int64_t)(-1 - d) * ld_s;
+    }
+};
+
 // G lanes per row, VEC floats per lane and chunk, KCH column chunks per lane (h <= G*VEC*KCH).
 // EXACT: h == G*VEC*KCH (no column guards).  IDX32: every element offset into x fits 32 bits.
-template <int G, int VEC, int KCH, bool EXACT, bool IDX32, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_spmm(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+template <int G, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, class Work>
+__global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const int32_t* __restrict__ col,
                                                          const float* __restrict__ val, const float* __restrict__ x,
-                                                         int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t n_rows,
-                                                         int h) {
+                                                         int64_t ldx, int64_t n_items, int h) {
     using V = Vec<VEC>;
     // (col, val) staging: one 8-byte slot per lane, double buffered so that one __syncwarp per chunk suffices
     __shared__ int2 s_e[2][kThreads];
@@ -58,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const int32_t* __restri
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int gbase = threadIdx.x & ~(G - 1);
     const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / G);
-    int64_t row = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    int64_t item = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G;
     const uint32_t ldx32 = (uint32_t)ldx;
 
     bool colok[KCH];
@@ -69,8 +100,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const int32_t* __restri
         colok[k] = EXACT || coff[k] < h;
     }
 
-    for (; row < n_rows; row += groups_per_grid) {
-        const int32_t e_begin = __ldg(rowptr + row), e_end = __ldg(rowptr + row + 1);
+    for (; item < n_items; item += groups_per_grid) {
+        int32_t e_begin, e_end;
+        float* yr;
+        work.get(item, e_begin, e_end, yr);
         typename V::T acc[KCH];
 #pragma unroll
         for (int k = 0; k < KCH; ++k) acc[k] = V::zero();
@@ -101,31 +134,92 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const int32_t* __restri
                     if (colok[k]) V::fma(acc[k], w, V::load(xr + coff[k]));
             }
         }
-        float* yr = y + row * ldy;
 #pragma unroll
         for (int k = 0; k < KCH; ++k)
             if (colok[k]) V::store(yr + coff[k], acc[k]);
     }
 }
 
+// y[long_row[i], :] = sum of its scratch rows, in chunk order (deterministic)
+__global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot,
+                               const int32_t* __restrict__ long_cnt, const float* __restrict__ scratch, int64_t ld_s,
+                               float* __restrict__ y, int64_t ldy, int h) {
+    const int i = blockIdx.x;
+    const int32_t r = long_row[i], s0 = long_slot[i], cnt = long_cnt[i];
+    for (int c = threadIdx.x; c < h; c += blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < cnt; ++k) acc += scratch[(int64_t)(s0 + k) * ld_s + c];
+        y[(int64_t)r * ldy + c] = acc;
+    }
+}
+
+struct Plan {   // host view of the arguments of glass_spmm_csr_planned
+    const int32_t *item_begin, *item_end, *item_dst;
+    int64_t n_items;
+    const int32_t *long_row, *long_slot, *long_cnt;
+    int64_t n_long;
+    float* scratch;
+};
+
 template <int G, int VEC, int KCH, int MINB = 4>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
-           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, cudaStream_t st) {
+           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
+    const int64_t n_items = plan ? plan->n_items : n_rows;
     const int64_t groups_per_block = kThreads / G;
-    int64_t blocks = ceil_div(n_rows, groups_per_block);
-    const int64_t cap = (int64_t)sm_count() * 8 * 4;  // a few waves of resident CTAs; rows are interleaved
+    int64_t blocks = ceil_div(n_items, groups_per_block);
+    const int64_t cap = (int64_t)sm_count() * 8 * 4;  // a few waves of resident CTAs; items are interleaved
     if (blocks > cap) blocks = cap;
     const bool exact = h == G * VEC * KCH;
     const bool idx32 = n_cols * ldx < (1ll << 31);
     const unsigned grid = (unsigned)blocks;
-#define GLASS_SPMM_GO(E, I) k_spmm<G, VEC, KCH, E, I, MINB><<<grid, kThreads, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, h)
+#define GLASS_SPMM_GO(E, I)                                                                                           \
+    do {                                                                                                              \
+        if (plan) {                                                                                                   \
+            PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h};          \
+            k_spmm<G, VEC, KCH, E, I, MINB, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);    \
+        } else {                                                                                                      \
+            RowWork w{rowptr, y, ldy};                                                                                \
+            k_spmm<G, VEC, KCH, E, I, MINB, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);     \
+        }                                                                                                             \
+    } while (0)
     if (exact && idx32) GLASS_SPMM_GO(true, true);
     else if (exact) GLASS_SPMM_GO(true, false);
     else if (idx32) GLASS_SPMM_GO(false, true);
     else GLASS_SPMM_GO(false, false);
 #undef GLASS_SPMM_GO
     GLASS_LAUNCH_CHECK();
+    if (plan && plan->n_long > 0) {
+        const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
+        k_spmm_combine<<<(unsigned)plan->n_long, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt,
+                                                                 plan->scratch, (int64_t)h, y, ldy, h);
+        GLASS_LAUNCH_CHECK();
+    }
     return GLASS_OK;
+}
+
+int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
+             int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
+    const bool vec = (h % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
+                     ((uintptr_t)y % 16 == 0) && (!plan || (uintptr_t)plan->scratch % 16 == 0);
+#define GO(G, V, K) return launch<G, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st)
+    if (vec) {
+        const int lanes = h / 4;
+        if (lanes <= 2) GO(2, 4, 1);
+        if (lanes <= 4) GO(4, 4, 1);
+        if (lanes <= 8) GO(8, 4, 1);
+        if (lanes <= 16) return launch<16, 4, 1, 5>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);
+        if (lanes <= 32) GO(32, 4, 1);
+        GO(32, 4, 2);
+    } else {
+        if (h <= 4) GO(4, 1, 1);
+        if (h <= 8) GO(8, 1, 1);
+        if (h <= 16) GO(16, 1, 1);
+        if (h <= 32) GO(32, 1, 1);
+        if (h <= 64) GO(32, 1, 2);
+        if (h <= 128) GO(32, 1, 4);
+        GO(32, 1, 8);
+    }
+#undef GO
 }
 
 }  // namespace
@@ -139,34 +233,95 @@ extern "C" int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const f
                     "spmm_csr: bad arguments");
     GLASS_CHECK_ARG(h <= 256, "spmm_csr: h=%d > 256 not supported", h);
     if (n_rows == 0) return GLASS_OK;
-    cudaStream_t st = as_stream(stream);
-    const bool vec = (h % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
-                     ((uintptr_t)y % 16 == 0);
-#define GO(G, V, K) return launch<G, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, st)
-    if (vec) {
-        const int lanes = h / 4;
-        if (lanes <= 2) GO(2, 4, 1);
-        if (lanes <= 4) GO(4, 4, 1);
-        if (lanes <= 8) GO(8, 4, 1);
-        if (lanes <= 16) {
-            static const int variant = getenv("GLASS_SPMM_VARIANT") ? atoi(getenv("GLASS_SPMM_VARIANT")) : 0;
-            switch (variant) {   // tuning knob: resident CTAs per SM (register cap)
-                case 1: return launch<16, 4, 1, 3>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, st);
-                case 2: return launch<16, 4, 1, 6>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, st);
-                case 3: return launch<16, 4, 1, 8>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, st);
-                default: return launch<16, 4, 1, 5>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, st);
-            }
+    return dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, nullptr, as_stream(stream));
+}
+
+// ---- row-splitting plan (init path; reads rowptr back to the host) ------------------------------------
+static int plan_host(const int32_t* rowptr_dev, int64_t n_rows, int max_len, std::vector<int32_t>& rp, cudaStream_t st) {
+    rp.resize((size_t)n_rows + 1);
+    GLASS_CUDA(cudaMemcpyAsync(rp.data(), rowptr_dev, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost, st));
+    GLASS_CUDA(cudaStreamSynchronize(st));
+    (void)max_len;
+    return GLASS_OK;
+}
+
+extern "C" int glass_spmm_plan_size(const int32_t* rowptr, int64_t n_rows, int max_len, int64_t* n_items_host,
+                                    int64_t* n_long_host, int64_t* n_slots_host, void* stream) {
+    GLASS_CHECK_ARG(rowptr && n_rows >= 0 && max_len >= 32 && n_items_host && n_long_host && n_slots_host,
+                    "spmm_plan_size: bad arguments");
+    std::vector<int32_t> rp;
+    int rc = plan_host(rowptr, n_rows, max_len, rp, as_stream(stream));
+    if (rc != GLASS_OK) return rc;
+    int64_t items = 0, nlong = 0, slots = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = rp[r + 1] - rp[r];
+        if (deg > max_len) {
+            const int64_t c = (deg + max_len - 1) / max_len;
+            items += c, slots += c, ++nlong;
+        } else {
+            ++items;
         }
-        if (lanes <= 32) GO(32, 4, 1);
-        GO(32, 4, 2);
-    } else {
-        if (h <= 4) GO(4, 1, 1);
-        if (h <= 8) GO(8, 1, 1);
-        if (h <= 16) GO(16, 1, 1);
-        if (h <= 32) GO(32, 1, 1);
-        if (h <= 64) GO(32, 1, 2);
-        if (h <= 128) GO(32, 1, 4);
-        GO(32, 1, 8);
     }
-#undef GO
+    *n_items_host = items, *n_long_host = nlong, *n_slots_host = slots;
+    return GLASS_OK;
+}
+
+extern "C" int glass_spmm_plan_build(const int32_t* rowptr, int64_t n_rows, int max_len, int32_t* item_begin,
+                                     int32_t* item_end, int32_t* item_dst, int32_t* long_row, int32_t* long_slot,
+                                     int32_t* long_cnt, void* stream) {
+    GLASS_CHECK_ARG(rowptr && n_rows >= 0 && max_len >= 32 && item_begin && item_end && item_dst,
+                    "spmm_plan_build: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    std::vector<int32_t> rp;
+    int rc = plan_host(rowptr, n_rows, max_len, rp, st);
+    if (rc != GLASS_OK) return rc;
+    std::vector<int32_t> ib, ie, id, lr, ls, lc;
+    // heavy items first (chunks of split rows), then one item per ordinary row
+    int32_t slot = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = rp[r + 1] - rp[r];
+        if (deg <= max_len) continue;
+        const int32_t c = (int32_t)((deg + max_len - 1) / max_len);
+        lr.push_back((int32_t)r), ls.push_back(slot), lc.push_back(c);
+        for (int32_t k = 0; k < c; ++k) {
+            const int32_t b = rp[r] + k * max_len;
+            ib.push_back(b);
+            ie.push_back(std::min<int32_t>(b + max_len, rp[r + 1]));
+            id.push_back(-1 - (slot + k));
+        }
+        slot += c;
+    }
+    for (int64_t r = 0; r < n_rows; ++r) {
+        if (rp[r + 1] - rp[r] > max_len) continue;
+        ib.push_back(rp[r]), ie.push_back(rp[r + 1]), id.push_back((int32_t)r);
+    }
+    auto up = [&](int32_t* dst, const std::vector<int32_t>& v) -> cudaError_t {
+        if (v.empty()) return cudaSuccess;
+        return cudaMemcpyAsync(dst, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, st);
+    };
+    GLASS_CUDA(up(item_begin, ib));
+    GLASS_CUDA(up(item_end, ie));
+    GLASS_CUDA(up(item_dst, id));
+    if (!lr.empty()) {
+        GLASS_CHECK_ARG(long_row && long_slot && long_cnt, "spmm_plan_build: long-row outputs missing");
+        GLASS_CUDA(up(long_row, lr));
+        GLASS_CUDA(up(long_slot, ls));
+        GLASS_CUDA(up(long_cnt, lc));
+    }
+    GLASS_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+    return GLASS_OK;
+}
+
+extern "C" int glass_spmm_csr_planned(const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
+                                      int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const int32_t* item_begin,
+                                      const int32_t* item_end, const int32_t* item_dst, int64_t n_items,
+                                      const int32_t* long_row, const int32_t* long_slot, const int32_t* long_cnt,
+                                      int64_t n_long, float* scratch, void* stream) {
+    GLASS_CHECK_ARG(col && val && x && y && n_rows >= 0 && n_cols > 0 && h > 0 && ldx >= h && ldy >= h && item_begin &&
+                        item_end && item_dst && n_items >= n_rows && (n_long == 0 || (long_row && long_slot && long_cnt && scratch)),
+                    "spmm_csr_planned: bad arguments");
+    GLASS_CHECK_ARG(h <= 256, "spmm_csr_planned: h=%d > 256 not supported", h);
+    if (n_items == 0) return GLASS_OK;
+    Plan p{item_begin, item_end, item_dst, n_items, long_row, long_slot, long_cnt, n_long, scratch};
+    return dispatch(nullptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, &p, as_stream(stream));
 }

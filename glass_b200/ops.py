@@ -102,6 +102,21 @@ def _spmm_csr_(rowptr, col, val, x, y):
 _define("spmm_csr_(Tensor rowptr, Tensor col, Tensor val, Tensor x, Tensor(a!) y) -> ()", _spmm_csr_)
 
 
+def _spmm_csr_planned_(col, val, x, y, item_begin, item_end, item_dst, long_row, long_slot, long_cnt, scratch):
+    lib = _lib.load()
+    n_rows, h = y.shape
+    check(lib.glass_spmm_csr_planned(_p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows, x.shape[0], h,
+                                     _p(item_begin), _p(item_end), _p(item_dst), item_begin.numel(), _p(long_row),
+                                     _p(long_slot), _p(long_cnt), long_row.numel(), _p(scratch), _stream()),
+          "spmm_csr_planned")
+    _count(2)
+
+
+_define("spmm_csr_planned_(Tensor col, Tensor val, Tensor x, Tensor(a!) y, Tensor item_begin, Tensor item_end, "
+        "Tensor item_dst, Tensor long_row, Tensor long_slot, Tensor long_cnt, Tensor(b!) scratch) -> ()",
+        _spmm_csr_planned_)
+
+
 def _pair_fwd_(a1, a2, w0, b0, w1, b1, mask, z_ratio, act, path, out, acts):
     lib = _lib.load()
     n, k1 = a1.shape
@@ -254,18 +269,56 @@ _ops = torch.ops.glass_b200
 # ---------------------------------------------------------------------------------------------
 # buildAdj -> CSR
 # ---------------------------------------------------------------------------------------------
+SPLIT_ROW_LEN = int(os.environ.get("GLASS_B200_SPLIT_ROW_LEN", "512"))
+
+
+class RowSplitPlan:
+    """Work items for a skewed CSR: rows longer than SPLIT_ROW_LEN entries are cut into chunks that are
+    reduced by separate lane groups (heavy items first) and summed in chunk order afterwards."""
+
+    def __init__(self, rowptr: torch.Tensor, max_len: int):
+        lib = _lib.load()
+        n_rows = rowptr.numel() - 1
+        sizes = [C.c_int64(0) for _ in range(3)]
+        check(lib.glass_spmm_plan_size(_p(rowptr), n_rows, max_len, *[C.byref(v) for v in sizes], _stream()),
+              "spmm_plan_size")
+        self.n_items, self.n_long, self.n_slots = (v.value for v in sizes)
+        i32 = dict(dtype=torch.int32, device=rowptr.device)
+        self.item_begin = torch.empty(self.n_items, **i32)
+        self.item_end = torch.empty(self.n_items, **i32)
+        self.item_dst = torch.empty(self.n_items, **i32)
+        self.long_row = torch.empty(self.n_long, **i32)
+        self.long_slot = torch.empty(self.n_long, **i32)
+        self.long_cnt = torch.empty(self.n_long, **i32)
+        if self.n_long:
+            check(lib.glass_spmm_plan_build(_p(rowptr), n_rows, max_len, _p(self.item_begin), _p(self.item_end),
+                                            _p(self.item_dst), _p(self.long_row), _p(self.long_slot),
+                                            _p(self.long_cnt), _stream()), "spmm_plan_build")
+
+
 class CSRAdj:
     """Normalised adjacency as CSR plus the CSR of its transpose (what buildAdj returns here).
 
     Stands in for the sparse COO tensor of impl/models.py:83-111: supports ``adj @ x``, ``.shape``
     and, for inspection, ``indices()`` / ``values()`` in coalesced COO form."""
 
-    def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr):
+    def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr, plan=None, plan_t=None):
         self.n, self.aggr = n, aggr
         self.rowptr, self.col, self.val = rowptr, col, val
         self.rowptr_t, self.col_t, self.val_t = rowptr_t, col_t, val_t
         self.deg = deg
         self.shape = (n, n)
+        self.plan, self.plan_t = plan, plan_t     # RowSplitPlan or None (no row longer than SPLIT_ROW_LEN)
+
+    def make_plans(self, max_len: int = None):
+        max_len = SPLIT_ROW_LEN if max_len is None else max_len
+        self.plan = self.plan_t = None
+        if self.n and self.col.numel():
+            p = RowSplitPlan(self.rowptr, max_len)
+            self.plan = p if p.n_long else None
+            p = RowSplitPlan(self.rowptr_t, max_len)
+            self.plan_t = p if p.n_long else None
+        return self
 
     @property
     def nnz(self) -> int:
@@ -284,7 +337,7 @@ class CSRAdj:
 
     def t(self):
         return CSRAdj(self.n, self.rowptr_t, self.col_t, self.val_t, self.rowptr, self.col, self.val, self.deg,
-                      self.aggr)
+                      self.aggr, self.plan_t, self.plan)
 
     def __matmul__(self, x):
         return spmm(self, x)
@@ -318,18 +371,27 @@ def build_csr(edge_index: torch.Tensor, edge_weight: torch.Tensor, n_node: int, 
     m = nnz_out.value
     if m != nnz:  # duplicates were merged
         col, val, col_t, val_t = col[:m].clone(), val[:m].clone(), col_t[:m].clone(), val_t[:m].clone()
-    return CSRAdj(n_node, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr)
+    return CSRAdj(n_node, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr).make_plans()
 
 
 # ---------------------------------------------------------------------------------------------
 # autograd building blocks
 # ---------------------------------------------------------------------------------------------
+def _run_spmm(rowptr, col, val, plan, x, y):
+    if plan is None:
+        _ops.spmm_csr_(rowptr, col, val, x, y)
+    else:
+        scratch = torch.empty((plan.n_slots, y.shape[1]), dtype=torch.float32, device=y.device)
+        _ops.spmm_csr_planned_(col, val, x, y, plan.item_begin, plan.item_end, plan.item_dst, plan.long_row,
+                               plan.long_slot, plan.long_cnt, scratch)
+
+
 class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj: CSRAdj):
         x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
         y = torch.empty((adj.n, x.shape[1]), dtype=torch.float32, device=x.device)
-        _ops.spmm_csr_(adj.rowptr, adj.col, adj.val, x, y)
+        _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, x, y)
         ctx.adj = adj
         return y
 
@@ -338,7 +400,7 @@ class _SpMM(torch.autograd.Function):
         adj = ctx.adj
         gy, _ = _rowmajor(gy)
         gx = torch.empty_like(gy, memory_format=torch.contiguous_format)
-        _ops.spmm_csr_(adj.rowptr_t, adj.col_t, adj.val_t, gy, gx)  # dX = A^T dY
+        _run_spmm(adj.rowptr_t, adj.col_t, adj.val_t, adj.plan_t, gy, gx)  # dX = A^T dY
         return gx, None
 
 

@@ -76,6 +76,23 @@ int glass_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t
 int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
                    int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h, void* stream);
 
+/* Skewed (power-law) graphs: rows longer than max_len entries are split into several work items whose
+ * partial sums go to a scratch matrix [n_slots, h] and are added up in chunk order (deterministic).
+ * Init path (reads rowptr back to the host): glass_spmm_plan_size returns the array sizes,
+ * glass_spmm_plan_build fills item_begin/item_end/item_dst [n_items] (heavy items first; item_dst >= 0 is
+ * a row of y, < 0 is scratch row -1-item_dst) and long_row/long_slot/long_cnt [n_long].
+ * glass_spmm_csr_planned is glass_spmm_csr driven by that plan (capturable; scratch from the caller). */
+int glass_spmm_plan_size(const int32_t* rowptr, int64_t n_rows, int max_len, int64_t* n_items_host,
+                         int64_t* n_long_host, int64_t* n_slots_host, void* stream);
+int glass_spmm_plan_build(const int32_t* rowptr, int64_t n_rows, int max_len, int32_t* item_begin,
+                          int32_t* item_end, int32_t* item_dst, int32_t* long_row, int32_t* long_slot,
+                          int32_t* long_cnt, void* stream);
+int glass_spmm_csr_planned(const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
+                           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const int32_t* item_begin,
+                           const int32_t* item_end, const int32_t* item_dst, int64_t n_items,
+                           const int32_t* long_row, const int32_t* long_slot, const int32_t* long_cnt,
+                           int64_t n_long, float* scratch, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Label-mixed pair of Linear layers  (impl/models.py:158-162 with activation, :169-173 without)
  *   p0 = act([a1|a2] W0^T + b0), p1 = act([a1|a2] W1^T + b1)

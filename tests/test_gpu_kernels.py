@@ -153,6 +153,34 @@ def test_spmm_skewed_rows_and_isolated_nodes():
         assert torch.count_nonzero(y[7]) == 0
 
 
+@pytest.mark.parametrize("h", [8, 17, 64, 128])
+def test_spmm_row_split_plan_matches_plain_kernel(h):
+    """Rows longer than the split length go through the planned kernel (chunk partials + ordered combine)."""
+    from glass_b200 import datasets, ops
+    n = 4000
+    e = datasets.powerlaw_edges(n, 50000, 1)
+    ei, ew = datasets.coalesce_undirected(e, torch.ones(e.shape[1]), n)
+    adj = ops.build_csr(ei.to(DEV), ew.to(DEV), n, "gcn")
+    x = torch.randn(n, h, generator=torch.Generator().manual_seed(2)).to(DEV)
+    gy = torch.randn(n, h, generator=torch.Generator().manual_seed(3)).to(DEV)
+    adj.plan = adj.plan_t = None
+    xg = x.clone().requires_grad_(True)
+    y0 = ops.spmm(adj, xg)
+    y0.backward(gy)
+    adj.make_plans(max_len=32)
+    assert adj.plan is not None and adj.plan.n_long > 10 and adj.plan.n_items > n
+    xs = x.clone().requires_grad_(True)
+    y1 = ops.spmm(adj, xs)
+    y1.backward(gy)
+    assert rel_err(y1.detach().cpu(), y0.detach().cpu()) < 1e-6
+    assert rel_err(xs.grad.cpu(), xg.grad.cpu()) < 1e-6
+    ref = O.build_adj(ei, ew, n, "gcn") @ x.cpu()
+    assert rel_err(y1.detach().cpu(), ref) < 1e-5
+    # uniform graphs need no plan
+    ei2, ew2 = rand_graph(2000, 20000, 5)
+    assert ops.build_csr(ei2.to(DEV), ew2.to(DEV), 2000, "sum").plan is None
+
+
 # ------------------------------------------------------------------------------------------ pair GEMM
 def _pair_ref(a, w0, b0, w1, b1, mask, z, act):
     f = {0: (lambda t: t), 1: torch.relu, 2: torch.nn.functional.elu}[act]
