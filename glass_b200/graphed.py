@@ -17,6 +17,17 @@ from . import utils
 from .dist import FlatGradAllReduce
 
 
+def allreduce_mean_coalesced(tensors, group=None):
+    """Average a list of tensors across ranks in place with one coalesced NCCL launch (capturable)."""
+    import torch.distributed as dist
+    if not tensors:
+        return
+    dev = tensors[0].device
+    with dist._coalescing_manager(group=group, device=dev, async_ops=False):
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+
+
 class GraphedTrainStep:
     def __init__(self, model, loss_fn: Callable, x, edge_index, edge_weight, pos_example: torch.Tensor,
                  y_example: torch.Tensor, lr: float, group=None, warmup: int = 3, betas=(0.9, 0.999), eps=1e-8,
@@ -29,10 +40,13 @@ class GraphedTrainStep:
         self.pos.copy_(pos_example)
         self.y.copy_(y_example)
         import torch.distributed as dist
-        world = dist.get_world_size(group) if dist.is_initialized() else 1
-        # one flat gradient buffer (single all-reduce) only when there is something to reduce; on one GPU
-        # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate pass)
-        self.flat = FlatGradAllReduce(model.parameters(), group) if world > 1 else None
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate
+        # pass); with several ranks those tensors are averaged in place by ONE coalesced NCCL all-reduce.
+        # (dist.FlatGradAllReduce is the staging-buffer variant used where coalescing is unavailable: gloo.)
+        self.flat = None
+        self.params = [p for p in model.parameters() if p.requires_grad]
         self.lr = torch.tensor(float(lr), device=dev)
         self.opt = torch.optim.Adam(model.parameters(), lr=self.lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                     capturable=True, fused=True)
@@ -57,8 +71,8 @@ class GraphedTrainStep:
             self.flat.zero()
         loss = self.loss_fn(self.model(self.x, self.ei, self.ew, self.pos, z, id=0), self.y)
         loss.backward()
-        if self.flat is not None:
-            self.flat.allreduce_mean()
+        if self.world > 1:
+            allreduce_mean_coalesced([p.grad for p in self.params if p.grad is not None], self.group)
         self.opt.step()
         self.loss.copy_(loss.detach())
 
@@ -95,6 +109,32 @@ class GraphedTrainStep:
         else:
             self.graph.replay()
         return self.loss
+
+
+class GraphedForward:
+    """Inference pass of impl/train.py:28-29 (labels + model.eval() forward) as one CUDA graph."""
+
+    def __init__(self, model, x, edge_index, edge_weight, pos_example: torch.Tensor, z_fn=utils.MaxZOZ, warmup: int = 2):
+        dev = x.device
+        self.model, self.x, self.ei, self.ew, self.z_fn = model, x, edge_index, edge_weight, z_fn
+        self.pos = torch.empty_like(pos_example, device=dev)
+        self.pos.copy_(pos_example)
+        model.eval()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self.out = self.model(self.x, self.ei, self.ew, self.pos, self.z_fn(self.x, self.pos))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = self.model(self.x, self.ei, self.ew, self.pos, self.z_fn(self.x, self.pos))
+
+    def __call__(self, pos: torch.Tensor) -> torch.Tensor:
+        self.pos.copy_(pos, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 def train_epoch(step: GraphedTrainStep, batches, sync_each_step: bool = True) -> float:

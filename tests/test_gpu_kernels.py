@@ -172,8 +172,8 @@ def test_spmm_row_split_plan_matches_plain_kernel(h):
     xs = x.clone().requires_grad_(True)
     y1 = ops.spmm(adj, xs)
     y1.backward(gy)
-    assert rel_err(y1.detach().cpu(), y0.detach().cpu()) < 1e-6
-    assert rel_err(xs.grad.cpu(), xg.grad.cpu()) < 1e-6
+    assert rel_err(y1.detach().cpu(), y0.detach().cpu()) < 5e-6   # chunked summation order
+    assert rel_err(xs.grad.cpu(), xg.grad.cpu()) < 5e-6
     ref = O.build_adj(ei, ew, n, "gcn") @ x.cpu()
     assert rel_err(y1.detach().cpu(), ref) < 1e-5
     # uniform graphs need no plan
