@@ -1,0 +1,109 @@
+"""Row-partitioned SpMM for graphs that should not be replicated (stress config:
+2M nodes / 100M undirected edges).  New capability -- the reference keeps the whole graph on one device.
+
+Rank r owns a contiguous block of rows of A (and of A^T), chosen so that every rank holds about the same
+number of stored entries (power-law graphs: balance nnz, not rows), plus the matching rows of every dense
+per-node matrix.  One exchange step per SpMM:
+
+    forward : all-gather the owners' feature rows -> local block SpMM        y_r  = A[rows_r, :]   @ X
+    backward: all-gather the owners' dY rows      -> local block SpMM        dX_r = A^T[rows_r, :] @ dY
+
+Feature shards are stored padded to the largest shard so that one `all_gather_into_tensor` (NCCL over
+NVLink) moves everything; the column indices of the local CSR blocks are remapped once to that padded
+layout.  GEMMs, label mix, pooling gathers are row-local and need no communication; GraphNorm needs one
+2C-value all-reduce of the column sums (not wired into the modules yet).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def balanced_row_splits(rowptr: torch.Tensor, parts: int) -> List[int]:
+    """Row boundaries [0 = b_0 <= b_1 <= ... <= b_P = N] with about nnz/P stored entries per block."""
+    n = rowptr.numel() - 1
+    nnz = int(rowptr[-1])
+    targets = torch.arange(1, parts, dtype=torch.float64) * (nnz / parts)
+    cuts = torch.searchsorted(rowptr.to(torch.float64).cpu(), targets).clamp(0, n).tolist()
+    bounds = [0] + [int(c) for c in cuts] + [n]
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def _block(rowptr, col, val, lo, hi, remap):
+    s, e = int(rowptr[lo]), int(rowptr[hi])
+    rp = (rowptr[lo:hi + 1] - rowptr[lo]).to(torch.int32).contiguous()
+    c = remap[col[s:e].long()].to(torch.int32).contiguous()
+    return rp, c, val[s:e].contiguous()
+
+
+class RowPartitionedAdj:
+    """This rank's row blocks of A and A^T with columns remapped to the padded all-gather layout."""
+
+    def __init__(self, adj: ops.CSRAdj, rank: int, world: int, group=None):
+        self.rank, self.world, self.group, self.n = rank, world, group, adj.n
+        dev = adj.col.device
+        self.bounds = balanced_row_splits(adj.rowptr, world)
+        sizes = [self.bounds[i + 1] - self.bounds[i] for i in range(world)]
+        self.rows = sizes[rank]
+        self.pad = max(max(sizes), 1)                       # rows per shard in the gathered buffer
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        # global row id -> row in the [world * pad, H] gathered matrix
+        owner = torch.bucketize(torch.arange(adj.n, device=dev), torch.tensor(self.bounds[1:-1], device=dev), right=True)
+        starts = torch.tensor(self.bounds[:-1], device=dev)
+        remap = owner * self.pad + (torch.arange(adj.n, device=dev) - starts[owner])
+        blk = _block(adj.rowptr, adj.col, adj.val, self.lo, self.hi, remap)
+        blk_t = _block(adj.rowptr_t, adj.col_t, adj.val_t, self.lo, self.hi, remap)
+        none = None
+        self.local = ops.CSRAdj(self.rows, *blk, *blk_t, none, adj.aggr)
+        self.local.make_plans()
+        self.nnz_local = int(blk[1].numel())
+        self.gather_override = None     # tests: callable(padded_local) -> [world * pad, H] without a process group
+
+    def shard(self, full: torch.Tensor) -> torch.Tensor:
+        """Rows of a replicated [N, H] matrix owned by this rank."""
+        return full[self.lo:self.hi].contiguous()
+
+    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        h = local.shape[1]
+        send = local
+        if self.rows != self.pad:
+            send = torch.zeros((self.pad, h), dtype=local.dtype, device=local.device)
+            send[:self.rows] = local
+        if self.gather_override is not None:
+            return self.gather_override(send.contiguous())
+        out = torch.empty((self.world * self.pad, h), dtype=local.dtype, device=local.device)
+        if self.world > 1:
+            dist.all_gather_into_tensor(out, send.contiguous(), group=self.group)
+        else:
+            out.copy_(send)
+        return out
+
+    def spmm(self, x_local: torch.Tensor) -> torch.Tensor:
+        """y_local = A[rows_r, :] @ X with X assembled from every rank's shard (differentiable)."""
+        return _PartSpMM.apply(x_local, self)
+
+
+class _PartSpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, part: RowPartitionedAdj):
+        ctx.part = part
+        x_full = part._gather(x_local)
+        y = torch.empty((part.rows, x_local.shape[1]), dtype=torch.float32, device=x_local.device)
+        a = part.local
+        ops._run_spmm(a.rowptr, a.col, a.val, a.plan, x_full, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        part = ctx.part
+        gy_full = part._gather(gy.contiguous())
+        gx = torch.empty((part.rows, gy.shape[1]), dtype=torch.float32, device=gy.device)
+        a = part.local
+        ops._run_spmm(a.rowptr_t, a.col_t, a.val_t, a.plan_t, gy_full, gx)
+        return gx, None
