@@ -32,7 +32,7 @@ def coalesce_undirected(edge: torch.Tensor, weight: torch.Tensor, n_node: int):
     col = torch.cat((edge[1], edge[0]))
     w = torch.cat((weight, weight))
     key, inv = torch.unique(row * n_node + col, sorted=True, return_inverse=True)
-    out_w = torch.zeros(key.numel(), dtype=weight.dtype).index_add_(0, inv, w)
+    out_w = torch.zeros(key.numel(), dtype=weight.dtype, device=weight.device).index_add_(0, inv, w)
     return torch.stack((torch.div(key, n_node, rounding_mode="floor"), key % n_node)), out_w
 
 
@@ -138,6 +138,28 @@ def powerlaw_edges(n: int, n_und: int, seed: int, alpha: float = 2.1) -> torch.T
     return torch.from_numpy(np.stack((got // n, got % n)))
 
 
+def powerlaw_edges_torch(n: int, n_und: int, seed: int, device, alpha: float = 2.1) -> torch.Tensor:
+    """Same Chung-Lu construction as powerlaw_edges, vectorised in torch so that the 100M-edge stress graph
+    is generated on the GPU in about a second (numpy needs minutes).  Different RNG stream than the numpy
+    generator: the two produce different (equally distributed) graphs."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    wgt = torch.arange(1, n + 1, dtype=torch.float64, device=device) ** (-1.0 / (alpha - 1.0))
+    cdf = torch.cumsum(wgt, 0)
+    cdf /= cdf[-1].clone()
+    perm = torch.randperm(n, generator=g, device=device)
+    got = torch.zeros(0, dtype=torch.int64, device=device)
+    while got.numel() < n_und:
+        m = int((n_und - got.numel()) * 1.3) + 1024
+        a = perm[torch.searchsorted(cdf, torch.rand(m, generator=g, device=device, dtype=torch.float64)).clamp_(max=n - 1)]
+        b = perm[torch.searchsorted(cdf, torch.rand(m, generator=g, device=device, dtype=torch.float64)).clamp_(max=n - 1)]
+        keep = a != b
+        lo, hi = torch.minimum(a, b)[keep], torch.maximum(a, b)[keep]
+        got = torch.unique(torch.cat((got, lo * n + hi)))
+        del a, b, keep, lo, hi
+    got = got[torch.randperm(got.numel(), generator=g, device=device)[:n_und]]
+    return torch.stack((torch.div(got, n, rounding_mode="floor"), got % n))
+
+
 def _random_subgraphs(n, count, mean_len, std_len, min_len, seed):
     g = np.random.default_rng(seed)
     rows = []
@@ -161,11 +183,15 @@ _SHAPES = {
 }
 
 
-def synthetic_graph(name: str, seed: int = 0) -> "BaseGraph":
-    """Seeded synthetic stand-ins for the datasets that are not shipped."""
+def synthetic_graph(name: str, seed: int = 0, device=None) -> "BaseGraph":
+    """Seeded synthetic stand-ins for the datasets that are not shipped.
+    With a CUDA `device`, power-law graphs are generated on the GPU (stress graph: seconds instead of minutes)."""
     s = _SHAPES[name]
-    gen = powerlaw_edges if s.get("gen") == "powerlaw" else uniform_edges
-    e = gen(s["n"], s["e"], seed)
+    if device is not None and s.get("gen") == "powerlaw":
+        e = powerlaw_edges_torch(s["n"], s["e"], seed, device)
+    else:
+        gen = powerlaw_edges if s.get("gen") == "powerlaw" else uniform_edges
+        e = gen(s["n"], s["e"], seed)
     rows = _random_subgraphs(s["n"], s["s"], s["mean"], s["std"], s["lmin"], seed + 1)
     g = np.random.default_rng(seed + 2)
     label = torch.from_numpy(g.integers(0, s["classes"], s["s"]))
@@ -173,7 +199,7 @@ def synthetic_graph(name: str, seed: int = 0) -> "BaseGraph":
     n_val = int(0.1 * s["s"])
     mask = torch.cat((torch.zeros(n_trn, dtype=torch.int64), torch.ones(n_val, dtype=torch.int64),
                       2 * torch.ones(s["s"] - n_trn - n_val, dtype=torch.int64)))
-    return BaseGraph(torch.empty((s["n"], 1, 0)), e, torch.ones(e.shape[1]), _pad_rows(rows),
+    return BaseGraph(torch.empty((s["n"], 1, 0)), e, torch.ones(e.shape[1], device=e.device), _pad_rows(rows),
                      label.to(torch.float) if s["classes"] == 2 else label, mask)
 
 
@@ -183,7 +209,7 @@ def synthetic_embedding(n: int, dim: int, seed: int = 0, std: float = 2.0) -> to
     return torch.randn(n, dim, generator=g) * std
 
 
-def load_dataset(name: str, seed: Optional[int] = None) -> "BaseGraph":
+def load_dataset(name: str, seed: Optional[int] = None, device=None) -> "BaseGraph":
     """datasets.py:103-126 for the shipped synthetic sets; seeded generators for the *_shaped ones.
 
     For shipped sets the split permutation is drawn from torch's global RNG exactly as the
@@ -202,5 +228,5 @@ def load_dataset(name: str, seed: Optional[int] = None) -> "BaseGraph":
         e = torch.from_numpy(d["edge"].astype(np.int64))
         return BaseGraph(torch.empty((n, 1, 0)), e, torch.ones(e.shape[1]), pad, label, mask)
     if name in _SHAPES:
-        return synthetic_graph(name, 0 if seed is None else seed)
+        return synthetic_graph(name, 0 if seed is None else seed, device)
     raise NotImplementedError(name)

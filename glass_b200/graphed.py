@@ -14,7 +14,6 @@ from typing import Callable, Optional
 import torch
 
 from . import utils
-from .dist import FlatGradAllReduce
 
 
 def allreduce_mean_coalesced(tensors, group=None):
@@ -44,8 +43,7 @@ class GraphedTrainStep:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate
         # pass); with several ranks those tensors are averaged in place by ONE coalesced NCCL all-reduce.
-        # (dist.FlatGradAllReduce is the staging-buffer variant used where coalescing is unavailable: gloo.)
-        self.flat = None
+        # (dist.FlatGradAllReduce is the staging-buffer variant for backends without coalescing: gloo.)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.lr = torch.tensor(float(lr), device=dev)
         self.opt = torch.optim.Adam(model.parameters(), lr=self.lr, betas=betas, eps=eps, weight_decay=weight_decay,
@@ -65,10 +63,7 @@ class GraphedTrainStep:
     # one iteration of impl/train.py:10-16
     def _step_eager(self):
         z = self.z_fn(self.x, self.pos)
-        if self.flat is None:
-            self.opt.zero_grad(set_to_none=True)
-        else:
-            self.flat.zero()
+        self.opt.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model(self.x, self.ei, self.ew, self.pos, z, id=0), self.y)
         loss.backward()
         if self.world > 1:
@@ -82,8 +77,6 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step_eager()
-        if self.flat is not None:
-            self.flat.check_views()
         return self
 
     def reset_to(self, state_dict):

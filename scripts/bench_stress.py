@@ -29,7 +29,7 @@ def main():
     from glass_b200 import datasets, ops
     from glass_b200.partition import RowPartitionedAdj
     t0 = time.time()
-    g = datasets.load_dataset(args.graph)
+    g = datasets.load_dataset(args.graph, device=dev)      # generated on the GPU (same seed on every rank)
     n, h = g.num_nodes, 64
     t_gen = time.time() - t0
     t0 = time.time()

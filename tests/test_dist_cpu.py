@@ -54,3 +54,16 @@ def test_shard_batches_drops_remainder():
     assert shard_batches(7, 0, 2) == [0, 2, 4] and shard_batches(7, 1, 2) == [1, 3, 5]
     assert shard_batches(5, 0, 1) == [0, 1, 2, 3, 4]
     assert shard_batches(3, 3, 4) == []
+
+
+def test_balanced_row_splits_balance_entries_not_rows():
+    from glass_b200.partition import balanced_row_splits
+    # 1000 rows: the first 10 hold half of all entries
+    deg = torch.cat((torch.full((10,), 500), torch.full((990,), 5)))
+    rowptr = torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(deg, 0))).to(torch.int32)
+    for parts in (1, 2, 4, 8):
+        b = balanced_row_splits(rowptr, parts)
+        assert b[0] == 0 and b[-1] == 1000 and len(b) == parts + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        nnz = [int(rowptr[b[i + 1]] - rowptr[b[i]]) for i in range(parts)]
+        assert max(nnz) <= int(rowptr[-1]) / parts + 500
+    assert balanced_row_splits(rowptr, 2)[1] <= 11      # the 10 hub rows alone fill the first half
