@@ -283,3 +283,26 @@ def test_cuda_graph_step_matches_eager_steps():
         assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (eager, graphed)
     for k, v in m1.state_dict().items():
         assert rel_err(m2.state_dict()[k].cpu(), v.cpu()) < 1e-3, k
+
+
+def test_cuda_graph_replays_draw_fresh_dropout_masks():
+    """torch's graph-safe Philox state advances on every replay: two replays of the same batch with
+    dropout 0.5 must see different keep masks (different losses), and lr changes must take effect."""
+    from glass_b200.graphed import GraphedForward, GraphedTrainStep
+    c = load_model_case("emuser_like")
+    x, ei, ew, pos, _ = _dev(c)
+    y = c["y"].to(DEV)
+    m = _product_from_case(c, dropout=0.5).train()
+    step = GraphedTrainStep(m, O.loss_fn_for(True), x, ei, ew, pos, y, lr=0.0).capture()   # lr 0: weights frozen
+    losses = [float(step(pos, y)) for _ in range(4)]
+    assert len({round(v, 6) for v in losses}) > 1, losses
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    step.set_lr(1e-2)
+    step(pos, y)
+    assert any(not torch.equal(before[k], v) for k, v in m.state_dict().items())
+    # graphed inference equals eager inference
+    m.eval()
+    with torch.no_grad():
+        ref = m(x, ei, ew, pos, None)
+    fwd = GraphedForward(m, x, ei, ew, pos, z_fn=lambda a, b: None)
+    assert torch.allclose(fwd(pos), ref, rtol=1e-5, atol=1e-6)
