@@ -306,3 +306,32 @@ def test_cuda_graph_replays_draw_fresh_dropout_masks():
         ref = m(x, ei, ew, pos, None)
     fwd = GraphedForward(m, x, ei, ew, pos, z_fn=lambda a, b: None)
     assert torch.allclose(fwd(pos), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_edge_cases_single_subgraph_empty_rows_and_tiny_graph():
+    """B = 1, a one-node subgraph, an all-padding row in the middle, and a 3-node graph."""
+    import functools
+
+    import torch.nn as nn
+
+    from glass_b200 import models, utils
+    n = 3
+    ei = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]], device=DEV)
+    ew = torch.ones(4, device=DEV)
+    x = torch.arange(n, device=DEV).reshape(n, 1, 1)
+    conv = models.EmbZGConv(8, 8, 2, max_deg=n - 1, activation=nn.ELU(inplace=True), jk=1, dropout=0.0,
+                            conv=functools.partial(models.GLASSConv, aggr="mean", z_ratio=0.8, dropout=0.0), gn=True)
+    m = models.GLASS(conv, nn.ModuleList([nn.Linear(16, 2)]), nn.ModuleList([models.MeanPool()])).to(DEV).train()
+    for pos in (torch.tensor([[2]], device=DEV), torch.tensor([[0, 1, -1], [-1, -1, -1], [2, -1, -1]], device=DEV)):
+        z = utils.MaxZOZ(x, pos)
+        out = m(x, ei, ew, pos, z)
+        assert out.shape == (pos.shape[0], 2) and torch.isfinite(out).all()
+        out.sum().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # oracle agrees on the ragged batch
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    cfg = O.GlassConfig(hidden_dim=8, conv_layer=2, aggr="mean", z_ratio=0.8, pool="mean", jk=True, out_dim=2)
+    posc = torch.tensor([[0, 1, -1], [2, -1, -1]])
+    ref, _, _ = O.glass_forward(sd, x.cpu(), O.build_adj(ei.cpu(), ew.cpu(), n, "mean"), posc, O.max_zero_one(n, posc), cfg)
+    got = m.eval()(x, ei, ew, posc.to(DEV), utils.MaxZOZ(x, posc.to(DEV)))
+    assert rel_err(got.detach().cpu(), ref) < 1e-4
