@@ -1,6 +1,6 @@
 #!/bin/bash
 # time SpMM tuning variants at the em_user shape with CUDA events (L2 flushed between launches)
-for v in 0 1 2 3 4 5 6; do
+for v in ${VARIANTS:-0 1 2 3 4}; do
 GLASS_SPMM_VARIANT=$v python - <<PY
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
