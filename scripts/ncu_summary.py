@@ -39,11 +39,13 @@ def launch_list(path, anchor="k_scatter_ones"):
     total = sum(t for _, t in seg)
     agg = collections.OrderedDict()
     for k, t in seg:
-        name = k.split("(")[0].split("::")[-1][-60:]
+        import re
+        m = re.search(r"(k_[A-Za-z0-9_]+(?:<[^>]*>)?)", k)
+        name = m.group(1)[:60] if m else k.split("(")[0].split("::")[-1][-60:]
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += t
-    print(f"one train step (eager, under ncu: cold cache, serialised): {len(seg)} launches, {total/1e3:.1f} us")
+    print(f"one train step (under ncu: cold cache, serialised): {len(seg)} launches, {total/1e3:.1f} us")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{t/1e3:9.1f} us  {100*t/total:5.1f} %  x{c:<3d} {k}")
 
