@@ -159,6 +159,7 @@ struct TcParams {
     int ndim;     // N of the MMA (forward: 2h, backward: k1+k2)
     int stages;
     uint32_t tmem_cols;
+    int rows_per_tile;   // <= BM: rows a tile owns (chosen so that every CTA runs the same number of tiles)
 };
 
 template <bool BWD>
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t n_tiles = (P.n + BM - 1) / BM;
+    const int RT = P.rows_per_tile;
+    const int64_t n_tiles = (P.n + RT - 1) / RT;
 
     if (warp < kEpiWarps) {
         // ================================ epilogue ==========================================
@@ -240,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             mbar_wait(smem_u32(tfull + acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const int quad = warp & 3, half = warp >> 2;         // TMEM lane quadrant (== warp % 4), column half
-            const int64_t row = tile * BM + quad * 32 + lane;
-            const bool row_ok = row < P.n;
+            const int64_t row = tile * RT + quad * 32 + lane;
+            const bool row_ok = row < P.n && quad * 32 + lane < RT;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N);
             if (!BWD) {
                 float c0 = 0.f, c1 = 0.f;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             for (int i = 0; i < kCPT; ++i) {
                 const int q = lt + i * kLoadThreads;
                 const int r = q >> 3, ch = q & 7;
-                const int64_t row = tile * BM + r;
+                const int64_t row = r < RT ? tile * RT + r : P.n;   // rows past the tile's share load nothing
                 const int k = kb * KBF + ch * 4;
                 rw.g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (BWD) {
@@ -735,8 +737,16 @@ int launch(TcParams& P, cudaStream_t st) {
         GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_done[BWD] = true;
     }
-    const int64_t tiles = ceil_div(P.n, BM);
+    // equal work per CTA: with 128-row tiles 57,333 rows are 448 tiles = 3.03 per SM, i.e. four rounds for a
+    // few CTAs; shrink the rows a tile owns so that every CTA runs exactly ceil(tiles / #SMs) tiles
     int grid = sm_count();
+    const int64_t full_tiles = ceil_div(P.n, BM);
+    if (grid > full_tiles) grid = (int)full_tiles;
+    const int64_t rounds = ceil_div(full_tiles, grid);
+    int rt = (int)ceil_div(P.n, (int64_t)grid * rounds);
+    if (rt > BM) rt = BM;
+    P.rows_per_tile = rt;
+    const int64_t tiles = ceil_div(P.n, rt);
     if (grid > tiles) grid = (int)tiles;
     k_pair_tc<BWD><<<grid, kThreads, bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
