@@ -19,6 +19,8 @@
 // The weight operand (both weight sets, hi and lo) stays resident in shared memory for the CTA's lifetime;
 // the row operand streams through a ring of 32-float K-blocks.  Two accumulators (2 x N TMEM columns)
 // overlap the epilogue of tile i with the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace glass {
@@ -160,7 +162,12 @@ struct TcParams {
     int stages;
     uint32_t tmem_cols;
     int rows_per_tile;   // <= BM: rows a tile owns (chosen so that every CTA runs the same number of tiles)
-};
+    long long* dbg;      // optional timeline of CTA 0 (GLASS_B200_TC_TIMELINE): [0]=start [1]=setup done,
+};                       // [16+i] loader consumed K-block i, [80+i] MMA committed K-block i, [144+t] epilogue done tile t, [200]=end
+
+__device__ __forceinline__ void stamp(long long* dbg, int idx) {
+    if (dbg && blockIdx.x == 0) dbg[idx] = clock64();
+}
 
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [2H]: b0 | b1 (forward only), 16-byte aligned
 
+    if (threadIdx.x == 0) stamp(P.dbg, 0);
     // ---- one-time setup ------------------------------------------------------------------
     if (!BWD)
         for (int c = threadIdx.x; c < 2 * H; c += kThreads) s_bias[c] = c < H ? P.b0[c] : P.b1[c - H];
@@ -230,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(P.dbg, 1);
 
     const int RT = P.rows_per_tile;
     const int64_t n_tiles = (P.n + RT - 1) / RT;
@@ -305,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             }
             tc_fence_before();
             mbar_arrive(smem_u32(tempty + acc));
+            if (threadIdx.x == 0 && it < 50) stamp(P.dbg, 144 + it);
         }
     } else if (warp == kEpiWarps) {
         // ================================ MMA issuer ========================================
@@ -334,6 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
                     umma_commit(smem_u32(empty + stage));                  // frees the ring slot when the MMAs retire
+                    if (it * nkb + kb < 64) stamp(P.dbg, 80 + it * nkb + kb);
                     if (++stage == P.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                 }
             }
         };
-        int stage = 0;
+        int stage = 0, nconsumed = 0;
         uint32_t phase = 0;
         auto consume = [&](const Raw& rw, int kb_of_slot) {
             (void)kb_of_slot;
@@ -412,6 +423,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             }
             fence_proxy_async();
             mbar_arrive(smem_u32(full + stage));
+            if (lt == 0 && nconsumed < 64) stamp(P.dbg, 16 + nconsumed);
+            ++nconsumed;
             if (++stage == P.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -748,8 +761,29 @@ int launch(TcParams& P, cudaStream_t st) {
     P.rows_per_tile = rt;
     const int64_t tiles = ceil_div(P.n, rt);
     if (grid > tiles) grid = (int)tiles;
+    static const bool timeline = getenv("GLASS_B200_TC_TIMELINE") != nullptr;
+    long long* dbg = nullptr;
+    if (timeline) {
+        GLASS_CUDA(cudaMalloc(&dbg, 256 * sizeof(long long)));
+        GLASS_CUDA(cudaMemset(dbg, 0, 256 * sizeof(long long)));
+        P.dbg = dbg;
+    }
     k_pair_tc<BWD><<<grid, kThreads, bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
+    if (timeline) {   // debugging aid only: synchronises and prints CTA 0's event times in SM cycles
+        long long h[256];
+        GLASS_CUDA(cudaStreamSynchronize(st));
+        GLASS_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        fprintf(stderr, "[tc timeline bwd=%d k=%d n=%d rt=%d stages=%d] setup %lld end %lld\n  loader:", (int)BWD, P.kdim,
+                P.ndim, P.rows_per_tile, P.stages, h[1] - h[0], h[200] - h[0]);
+        for (int i = 0; i < 64 && h[16 + i]; ++i) fprintf(stderr, " %lld", h[16 + i] - h[0]);
+        fprintf(stderr, "\n  mma:");
+        for (int i = 0; i < 64 && h[80 + i]; ++i) fprintf(stderr, " %lld", h[80 + i] - h[0]);
+        fprintf(stderr, "\n  epilogue:");
+        for (int i = 0; i < 50 && h[144 + i]; ++i) fprintf(stderr, " %lld", h[144 + i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     return GLASS_OK;
 }
 
