@@ -12,7 +12,7 @@ buf = sm.empty(n, dtype=torch.float32, device=dev)
 hdl = sm.rendezvous(buf, dist.group.WORLD)
 gname = dist.group.WORLD.group_name
 if rank == 0:
-    print("multicast support:", hdl.has_multicast_support(dev.type, dev.index) if hasattr(hdl, "has_multicast_support") else None, "multicast_ptr", hdl.multicast_ptr)
+    print("multicast_ptr", hdl.multicast_ptr, "buffer_ptrs", [hex(p) for p in hdl.buffer_ptrs])
 
 def timeit(fn, reps=30, graph=False):
     for _ in range(3): fn()
