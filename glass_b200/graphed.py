@@ -16,15 +16,37 @@ import torch
 from . import utils
 
 
-def allreduce_mean_coalesced(tensors, group=None):
-    """Average a list of tensors across ranks in place with one coalesced NCCL launch (capturable)."""
-    import torch.distributed as dist
-    if not tensors:
-        return
-    dev = tensors[0].device
-    with dist._coalescing_manager(group=group, device=dev, async_ops=False):
-        for t in tensors:
-            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+class GradAverager:
+    """Averages gradients across ranks with as few NCCL launches as possible: every large tensor (the
+    trainable N x H embedding table is ~99 % of the bytes) is reduced in place, all small ones travel
+    through one persistent flat buffer (a coalesced group of 17 separate all-reduces costs ~100 us of
+    per-operation latency at N = 2; one 14.8 MB all-reduce costs 55 us).  Capturable in a CUDA graph."""
+
+    BIG = 1 << 18   # elements
+
+    def __init__(self, params, group=None):
+        self.group = group
+        self.small = [p for p in params if p.numel() < self.BIG]
+        self.big = [p for p in params if p.numel() >= self.BIG]
+        total = sum(p.numel() for p in self.small)
+        ref = params[0]
+        self.flat = torch.zeros(max(total, 1), dtype=ref.dtype, device=ref.device)
+        self.views, off = [], 0
+        for p in self.small:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def __call__(self):
+        import torch.distributed as dist
+        for p in self.big:
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+        pairs = [(v, p) for v, p in zip(self.views, self.small) if p.grad is not None]
+        if pairs:
+            torch._foreach_copy_([v for v, _ in pairs], [p.grad for _, p in pairs])
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            for v, p in pairs:      # the optimizer reads the averaged values straight from the flat buffer
+                p.grad = v
 
 
 class GraphedTrainStep:
@@ -42,9 +64,9 @@ class GraphedTrainStep:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate
-        # pass); with several ranks those tensors are averaged in place by ONE coalesced NCCL all-reduce.
-        # (dist.FlatGradAllReduce is the staging-buffer variant for backends without coalescing: gloo.)
+        # pass); with several ranks GradAverager averages them with two NCCL all-reduces (table + the rest).
         self.params = [p for p in model.parameters() if p.requires_grad]
+        self.averager = GradAverager(self.params, group) if self.world > 1 else None
         self.lr = torch.tensor(float(lr), device=dev)
         self.opt = torch.optim.Adam(model.parameters(), lr=self.lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                     capturable=True, fused=True)
@@ -66,8 +88,8 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model(self.x, self.ei, self.ew, self.pos, z, id=0), self.y)
         loss.backward()
-        if self.world > 1:
-            allreduce_mean_coalesced([p.grad for p in self.params if p.grad is not None], self.group)
+        if self.averager is not None:
+            self.averager()
         self.opt.step()
         self.loss.copy_(loss.detach())
 
