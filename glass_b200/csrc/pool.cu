@@ -45,6 +45,8 @@ struct BatchSeg {  // rows already gathered; batch sorted ascending -> segment =
 // lane order.  MAX keeps (value, position) and resolves ties towards the earliest position.
 constexpr int kPoolMaxThreads = 1024;
 
+constexpr int kPoolStage = 2048;   // segment entries staged in shared memory per pass
+
 template <class RowFn>
 __device__ __forceinline__ void pool_fwd_body(RowFn row_of, int64_t len, const float* __restrict__ emb, int64_t lde,
                                               int mode, float* __restrict__ out, float* __restrict__ cnt_out,
@@ -52,36 +54,69 @@ __device__ __forceinline__ void pool_fwd_body(RowFn row_of, int64_t len, const f
     __shared__ int s_cnt;
     __shared__ float s_val[kPoolMaxThreads];
     __shared__ int s_pos[kPoolMaxThreads];
+    __shared__ int s_row[kPoolStage];          // row id (or -1) of every staged segment entry
     const int CT = blockDim.x, LQ = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
-    if (tx == 0 && ty == 0) s_cnt = 0;
+    const int tid = ty * CT + tx, nthr = CT * LQ;
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
-    if (tx == 0) {
+    {   // valid entries of the whole segment
         int c = 0;
-        for (int64_t l = ty; l < len; l += LQ) c += row_of(l) >= 0;
+        for (int64_t l = tid; l < len; l += nthr) c += row_of(l) >= 0;
         if (c) atomicAdd(&s_cnt, c);
     }
     __syncthreads();
     const float cnt = (float)s_cnt;
-    if (tx == 0 && ty == 0 && cnt_out) cnt_out[b] = cnt;
+    if (tid == 0 && cnt_out) cnt_out[b] = cnt;
     const float coef = (mode == GLASS_POOL_SIZE && cnt > 0.f) ? size_coef(cnt) : 1.f;
-    for (int c0 = 0; c0 < d; c0 += CT) {
-        const int c = c0 + tx;
+    const int ncol_pass = (d + CT - 1) / CT;
+    for (int cp = 0; cp < ncol_pass; ++cp) {
+        const int c = cp * CT + tx;
         float acc = (mode == GLASS_POOL_MAX) ? -FLT_MAX : 0.f;
         int best = -1;
-        if (c < d) {
-            for (int64_t l = ty; l < len; l += LQ) {
-                const int64_t r = row_of(l);
-                if (r < 0) continue;
-                const float v = emb[r * lde + c];
-                if (mode == GLASS_POOL_MAX) {
-                    if (best < 0 || v > acc) {
-                        acc = v;
-                        best = (int)l;
+        for (int64_t l0 = 0; l0 < len; l0 += kPoolStage) {
+            const int chunk = (int)min((int64_t)kPoolStage, len - l0);
+            __syncthreads();
+            for (int i = tid; i < chunk; i += nthr) s_row[i] = (int)row_of(l0 + i);   // the id loads are independent
+            __syncthreads();
+            if (c < d) {
+                // row lane ty takes entries ty, ty+LQ, ...; four gathers in flight per thread
+                int i = ty;
+                for (; i + 3 * LQ < chunk; i += 4 * LQ) {
+                    int r[4];
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) r[u] = s_row[i + u * LQ];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = r[u] >= 0 ? emb[(int64_t)r[u] * lde + c] : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (r[u] < 0) continue;
+                        if (mode == GLASS_POOL_MAX) {
+                            if (best < 0 || v[u] > acc) {
+                                acc = v[u];
+                                best = (int)(l0 + i + u * LQ);
+                            }
+                        } else if (mode == GLASS_POOL_SIZE) {
+                            acc = __fadd_rn(acc, __fmul_rn(v[u], coef));
+                        } else {
+                            acc += v[u];
+                        }
                     }
-                } else if (mode == GLASS_POOL_SIZE) {
-                    acc = __fadd_rn(acc, __fmul_rn(v, coef));
-                } else {
-                    acc += v;
+                }
+                for (; i < chunk; i += LQ) {
+                    const int r = s_row[i];
+                    if (r < 0) continue;
+                    const float v = emb[(int64_t)r * lde + c];
+                    if (mode == GLASS_POOL_MAX) {
+                        if (best < 0 || v > acc) {
+                            acc = v;
+                            best = (int)(l0 + i);
+                        }
+                    } else if (mode == GLASS_POOL_SIZE) {
+                        acc = __fadd_rn(acc, __fmul_rn(v, coef));
+                    } else {
+                        acc += v;
+                    }
                 }
             }
         }
@@ -136,21 +171,30 @@ __device__ __forceinline__ float bwd_coef(int mode, float cnt) {
 __global__ void k_pool_pad_bwd(const float* __restrict__ dout, int64_t lddo, PadSeg seg, int mode,
                                const float* __restrict__ cnt, const int32_t* __restrict__ argmax,
                                float* __restrict__ demb, int64_t ldde, int d) {
+    __shared__ int s_row[kPoolStage];
     const int64_t b = blockIdx.x;
     const int CT = blockDim.x, LQ = blockDim.y;
-    for (int c = threadIdx.x; c < d; c += CT) {
-        const float g = dout[b * lddo + c];
-        if (mode == GLASS_POOL_MAX) {
-            if (threadIdx.y == 0) {
+    const int tid = threadIdx.y * CT + threadIdx.x, nthr = CT * LQ;
+    if (mode == GLASS_POOL_MAX) {
+        if (threadIdx.y == 0)
+            for (int c = threadIdx.x; c < d; c += CT) {
                 const int32_t a = argmax[b * (int64_t)d + c];
-                if (a >= 0) atomicAdd(demb + (int64_t)a * ldde + c, g);
+                if (a >= 0) atomicAdd(demb + (int64_t)a * ldde + c, dout[b * lddo + c]);
             }
-            continue;
-        }
-        const float gc = g * bwd_coef(mode, cnt[b]);
-        for (int64_t l = threadIdx.y; l < seg.lmax; l += LQ) {
-            const int64_t r = seg.row(b, l);
-            if (r >= 0) atomicAdd(demb + r * ldde + c, gc);  // nodes may belong to several subgraphs
+        return;
+    }
+    const float coef = bwd_coef(mode, cnt[b]);
+    for (int64_t l0 = 0; l0 < seg.lmax; l0 += kPoolStage) {
+        const int chunk = (int)min((int64_t)kPoolStage, seg.lmax - l0);
+        __syncthreads();
+        for (int i = tid; i < chunk; i += nthr) s_row[i] = (int)seg.row(b, l0 + i);
+        __syncthreads();
+        for (int c = threadIdx.x; c < d; c += CT) {
+            const float gc = dout[b * lddo + c] * coef;
+            for (int i = threadIdx.y; i < chunk; i += LQ) {
+                const int r = s_row[i];
+                if (r >= 0) atomicAdd(demb + (int64_t)r * ldde + c, gc);  // nodes may belong to several subgraphs
+            }
         }
     }
 }
