@@ -298,3 +298,110 @@ class GLASS(nn.Module):
         emb = self.NodeEmb(x, edge_index, edge_weight, z)
         emb = self.Pool(emb, subG_node, self.pools[id])
         return self.preds[id](emb)
+
+
+# --- plain (unlabeled) GNN used by the reference's link-prediction pre-training (GNNEmb.py) -----------
+# the single-weight-set subset of the same kernels.  A single Linear is run
+# through the label-mixed pair kernel with both slots bound to the same weights, every row "labelled" and
+# z = 1, which selects 1*p1 + 0*p0 == p1 exactly (the weight gradient is dW0 + dW1 = 0 + dW).
+def _single_linear(a1, a2, lin: nn.Linear, act: int):
+    ones = torch.ones(a1.shape[0], dtype=torch.uint8, device=a1.device)
+    return ops.pair_linear_mix(a1, a2, lin.weight, lin.bias, lin.weight, lin.bias, ones, 1.0, act)
+
+
+class MyGCNConv(nn.Module):
+    """impl/models.py:361-397: Linear + activation -> adj @ x -> GraphNorm -> [x | x_] -> Linear."""
+
+    def __init__(self, in_channels: int, out_channels: int, activation=nn.ReLU(inplace=True), aggr="mean"):
+        super().__init__()
+        self.trans_fn = nn.Linear(in_channels, out_channels)
+        self.comb_fn = nn.Linear(in_channels + out_channels, out_channels)
+        self.adj = None
+        self.activation = activation
+        self.aggr = aggr
+        self.gn = GraphNorm(out_channels)
+
+    def reset_parameters(self):
+        self.trans_fn.reset_parameters()
+        self.comb_fn.reset_parameters()
+        self.gn.reset_parameters()
+
+    def forward(self, x_, edge_index, edge_weight):
+        if self.adj is None:
+            self.adj = buildAdj(edge_index, edge_weight, x_.shape[0], self.aggr)
+        x = _single_linear(x_, None, self.trans_fn, _act_id(self.activation))              # :386-387
+        x = ops.spmm(self.adj, x)                                                          # :388
+        x = self.gn(x)                                                                     # :389
+        return _single_linear(x, x_, self.comb_fn, ACT_NONE)                               # :390-391
+
+
+class EmbGConv(nn.Module):
+    """impl/models.py:400-476.  The element-wise activation / dropout between layers of this pre-training
+    model are plain torch ops (it is not on the GLASS hot path); GEMMs, SpMM and GraphNorm use the kernels."""
+
+    def __init__(self, input_channels: int, hidden_channels: int, output_channels: int, num_layers: int, max_deg: int,
+                 dropout=0, activation=nn.ReLU(inplace=True), conv=MyGCNConv, gn=True, jk=False, **kwargs):
+        super().__init__()
+        self.input_emb = nn.Embedding(max_deg + 1, hidden_channels)
+        self.convs = nn.ModuleList()
+        self.jk = jk
+        if num_layers > 1:
+            self.convs.append(conv(in_channels=input_channels, out_channels=hidden_channels, **kwargs))
+            for _ in range(num_layers - 2):
+                self.convs.append(conv(in_channels=hidden_channels, out_channels=hidden_channels, **kwargs))
+            self.convs.append(conv(in_channels=hidden_channels, out_channels=output_channels, **kwargs))
+        else:
+            self.convs.append(conv(in_channels=input_channels, out_channels=output_channels, **kwargs))
+        self.activation = activation
+        self.dropout = dropout
+        if gn:
+            self.gns = nn.ModuleList()
+            for _ in range(num_layers - 1):
+                self.gns.append(GraphNorm(hidden_channels))
+        else:
+            self.gns = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        if self.gns is not None:
+            for gn in self.gns:
+                gn.reset_parameters()
+
+    def forward(self, x, edge_index, edge_weight, z=None):
+        import torch.nn.functional as F
+        xs = []
+        x = F.dropout(ops.embedding(x.reshape(-1), self.input_emb.weight), p=self.dropout, training=self.training)
+        for layer, conv in enumerate(self.convs[:-1]):
+            x = conv(x, edge_index, edge_weight)
+            if self.gns is not None:
+                x = self.gns[layer](x)
+            xs.append(x)
+            # like the reference, an in-place activation module also rewrites the tensor just appended to xs
+            x = F.dropout(self.activation(x), p=self.dropout, training=self.training)
+        xs.append(self.convs[-1](x, edge_index, edge_weight))
+        return torch.cat(xs, dim=-1) if self.jk else xs[-1]
+
+
+class EdgeGNN(nn.Module):
+    """impl/models.py:479-509: node embeddings -> mean of the two end points of each pair -> preds[id]."""
+
+    def __init__(self, conv, preds: nn.ModuleList, pools: nn.ModuleList):
+        super().__init__()
+        self.conv = conv
+        self.preds = preds
+        self.pools = pools
+
+    def NodeEmb(self, x, edge_index, edge_weight, z=None):
+        embs = [self.conv(x[:, c, :].reshape(x.shape[0], x.shape[-1]), edge_index, edge_weight, z)
+                for c in range(x.shape[1])]
+        return embs[0] if len(embs) == 1 else torch.mean(torch.stack(embs, dim=1), dim=1)
+
+    def Pool(self, emb, subG_node, pool):
+        return ops.segment_pool(emb, subG_node, "mean")      # emb[subG_node].mean(dim=1), impl/models.py:502-504
+
+    def forward(self, x, edge_index, edge_weight, subG_node, z=None, id=0):
+        emb = self.NodeEmb(x, edge_index, edge_weight, z)
+        emb = self.Pool(emb, subG_node, self.pools[id])
+        return self.preds[id](emb)

@@ -199,6 +199,37 @@ def gen_models():
         print(name, "loss", float(loss), "logits", logits.flatten()[:3].tolist())
 
 
+def gen_edgegnn():
+    """EmbGConv(MyGCNConv) + EdgeGNN (impl/models.py:361-509; built as in GNNEmb.py:76-100)."""
+    torch.manual_seed(77)
+    n, H, L = 300, 32, 2
+    ei = torch.from_numpy(random_graph(n, 1500, 9))
+    ew = torch.ones(ei.shape[1])
+    x = torch.randint(0, 12, (n, 1, 1))
+    conv = models.EmbGConv(H, H, H, L, max_deg=11, activation=nn.ReLU(inplace=True), jk=True, dropout=0.0,
+                           conv=functools.partial(models.MyGCNConv, aggr="mean", activation=nn.ReLU(inplace=True)), gn=True)
+    mlp = nn.Linear(H * L, 1)
+    model = models.EdgeGNN(conv, nn.ModuleList([mlp]), nn.ModuleList([models.MeanPool()]))
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if "gn" in k:
+                p.add_(0.3 * torch.randn_like(p))
+    sd0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    pairs = torch.randint(0, n, (40, 2))
+    y = (torch.rand(40) > 0.5).float()
+    model.train()
+    logits = model(x, ei, ew, pairs)
+    loss = nn.BCEWithLogitsLoss()(logits.flatten(), y)
+    model.zero_grad()
+    loss.backward()
+    out = {f"sd.{k}": v for k, v in sd0.items()}
+    out.update({f"grad.{k}": p.grad.detach().numpy() for k, p in model.named_parameters()})
+    out.update(ei=ei.numpy(), ew=ew.numpy(), x=x.numpy(), pairs=pairs.numpy(), y=y.numpy(),
+               logits=logits.detach().numpy(), loss=np.float32(loss.item()))
+    np.savez_compressed(os.path.join(HERE, "model_edgegnn.npz"), **out)
+    print("edgegnn loss", float(loss))
+
+
 # ------------------------------------------------------------------------------------------
 def gen_density_trajectory(n_steps=62, nodeid=False):
     """Seed-0 loss trajectory of the unmodified reference on the shipped density config
@@ -275,6 +306,7 @@ if __name__ == "__main__":
     gen_utils()
     gen_buildadj()
     gen_models()
+    gen_edgegnn()
     gen_density_trajectory()
     gen_density_trajectory(n_steps=40, nodeid=True)
     print("golden fixtures:", sorted(f for f in os.listdir(HERE) if f.endswith((".npz", ".json"))))

@@ -335,3 +335,29 @@ def test_edge_cases_single_subgraph_empty_rows_and_tiny_graph():
     ref, _, _ = O.glass_forward(sd, x.cpu(), O.build_adj(ei.cpu(), ew.cpu(), n, "mean"), posc, O.max_zero_one(n, posc), cfg)
     got = m.eval()(x, ei, ew, posc.to(DEV), utils.MaxZOZ(x, posc.to(DEV)))
     assert rel_err(got.detach().cpu(), ref) < 1e-4
+
+
+def test_pretraining_modules_match_reference_golden():
+    """MyGCNConv / EmbGConv / EdgeGNN (impl/models.py:361-509) vs the reference."""
+    import functools
+
+    import torch.nn as nn
+
+    from glass_b200 import models
+    d = np.load(os.path.join(GOLDEN, "model_edgegnn.npz"))
+    H, L = 32, 2
+    conv = models.EmbGConv(H, H, H, L, max_deg=11, activation=nn.ReLU(inplace=True), jk=True, dropout=0.0,
+                           conv=functools.partial(models.MyGCNConv, aggr="mean", activation=nn.ReLU(inplace=True)), gn=True)
+    m = models.EdgeGNN(conv, nn.ModuleList([nn.Linear(H * L, 1)]), nn.ModuleList([models.MeanPool()]))
+    sd = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd.")}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    t = lambda k: torch.from_numpy(d[k]).to(DEV)
+    logits = m(t("x"), t("ei"), t("ew"), t("pairs"))
+    loss = nn.BCEWithLogitsLoss()(logits.flatten(), t("y"))
+    loss.backward()
+    assert rel_err(logits.detach().cpu(), d["logits"]) < TOL
+    assert abs(float(loss) - float(d["loss"])) < TOL
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad.cpu(), d[f"grad.{k}"]) < TOL, k
