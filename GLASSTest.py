@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from torch.optim import Adam, lr_scheduler
 
-from glass_b200 import SubGDataset, config, datasets, run, train, utils
+from glass_b200 import SubGDataset, config, datasets, ops, run, train, utils
 from glass_b200.graphed import GraphedTrainStep, train_epoch
 
 
@@ -41,6 +41,7 @@ def set_seed(seed: int):
     np.random.seed(seed)
     torch.manual_seed(seed)
     torch.cuda.manual_seed_all(seed)
+    ops.manual_seed(seed)       # in-kernel dropout generator
 
 
 class Experiment:

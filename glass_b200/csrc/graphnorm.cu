@@ -2,7 +2,7 @@
 // fused with the activation / dropout the reference applies right after it (:166, :251, :258-259).
 //
 //   mu = mean_rows(x); o = x - mean_scale*mu; var = mean_rows(o^2) = E[x^2] - (2a - a^2) mu^2
-//   out = keep * pscale * act(weight * o / sqrt(var + eps) + bias)
+//   out = keep * 1/(1-p) * act(weight * o / sqrt(var + eps) + bias)     (keep: explicit mask or Philox bits)
 //
 // Forward = column sums of x and x^2 (fp64 accumulators, per-CTA partials reduced in CTA order, so the
 // result is run-to-run deterministic) -> per-column constants -> one elementwise pass.
@@ -20,7 +20,63 @@ constexpr int kThreads = 256;
 constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs; fixed so the workspace size is device independent
 
 // stats rows
-enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4 };
+enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4, ST_RNG = 5 };
+
+// Dropout keep decision.  Either an explicit uint8 mask (tests inject one so that a train-mode pass can be
+// compared element-wise with the oracle) or a counter-based generator: Philox4x32-10 keyed by a per-device
+// seed, with counter = (element index / 4, id of this GraphNorm call).  The call id is drawn from a device
+// counter by the finalize kernel and stored with the statistics, so backward regenerates the same bits and a
+// CUDA-graph replay draws fresh ones -- no mask tensor is written or read.
+struct Drop {
+    const uint8_t* keep;                 // explicit mask [n, c] or NULL
+    const unsigned long long* rng;       // {seed, call counter} in device memory or NULL
+    float pscale;                        // 1 / (1 - p)
+    uint32_t thresh;                     // drop iff u32 < thresh  (thresh = p * 2^32)
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+struct DropCtx {   // per-thread constants of the generator
+    uint2 key;
+    uint32_t call_lo, call_hi;
+};
+__device__ __forceinline__ DropCtx drop_ctx(const Drop& d, const float* stats, int c) {
+    DropCtx x{};
+    if (!d.keep && d.rng) {
+        const unsigned long long seed = d.rng[0];
+        x.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        x.call_lo = __float_as_uint(stats[ST_RNG * c + 0]);
+        x.call_hi = c > 1 ? __float_as_uint(stats[ST_RNG * c + 1]) : 0u;
+    }
+    return x;
+}
+// multipliers (pscale or 0) of the VEC consecutive elements starting at linear index `lin` (row * c + col)
+template <int VEC>
+__device__ __forceinline__ void drop_mult(const Drop& d, const DropCtx& x, int64_t lin, float (&m)[VEC]) {
+    if (d.keep) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) m[k] = d.keep[lin + k] ? d.pscale : 0.f;
+    } else if (d.rng) {
+        const uint64_t grp = (uint64_t)lin >> 2;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), x.call_lo, x.call_hi), x.key);
+        const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) m[k] = u[((int)(lin & 3) + k) & 3] < d.thresh ? 0.f : d.pscale;
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) m[k] = 1.f;
+    }
+}
 
 // Finalisation: one warp per column; lane l adds partials l, l+32, ... in order (all loads issued up
 // front), then a fixed butterfly -> deterministic.  (A "last CTA finalises" variant was measured slower:
@@ -91,8 +147,9 @@ __device__ __forceinline__ void finalize_bwd_col(const Fin& f, double s1, double
 template <int VEC, bool BWD>
 __global__ void __launch_bounds__(kThreads)
 k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dout, int64_t lddo,
-          const float* __restrict__ stats, const float* __restrict__ bias, int act, const uint8_t* __restrict__ keep,
-          float pscale, int64_t n, int c, double* __restrict__ partial) {
+          const float* __restrict__ stats, const float* __restrict__ bias, int act, const Drop drop, int64_t n, int c,
+          double* __restrict__ partial) {
+    const DropCtx dctx = BWD ? drop_ctx(drop, stats, c) : DropCtx{};
     // thread -> (column vector cvl, row lane rl).  CVB column vectors are processed per pass.
     const int CV = (c + VEC - 1) / VEC;
     const int CVB = CV < kThreads ? CV : kThreads;
@@ -132,6 +189,8 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
                     xv[0] = x[r * ldx + col];
                     if (BWD) gv[0] = dout[r * lddo + col];
                 }
+                float dm[VEC];
+                if (BWD) drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     if (!BWD) {
@@ -140,8 +199,7 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
                     } else {
                         float o = xv[k] - am[k];
                         float pre = fmaf(sc[k], o, bs[k]);
-                        float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act);
-                        if (keep) u *= keep[r * (int64_t)c + col + k] ? pscale : 0.f;
+                        float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
                         s[k] += (double)u;
                         q[k] += (double)u * (double)(o * rs[k]);
                     }
@@ -173,7 +231,14 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(128) k_gn_finalize(const double* partial, int nblk, int64_t n, int c, const Fin fin) {
+__global__ void __launch_bounds__(128) k_gn_finalize(const double* partial, int nblk, int64_t n, int c, const Fin fin,
+                                                     unsigned long long* rng) {
+    if (!BWD && rng && blockIdx.x == 0 && threadIdx.x == 0) {   // id of this call for the dropout generator
+        const unsigned long long id = rng[1];
+        rng[1] = id + 1;
+        fin.stats[ST_RNG * c + 0] = __uint_as_float((uint32_t)id);
+        if (c > 1) fin.stats[ST_RNG * c + 1] = __uint_as_float((uint32_t)(id >> 32));
+    }
     const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (col >= c) return;
     double a, b;
@@ -186,8 +251,8 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const double* partial, int 
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_gn_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ stats, const float* __restrict__ bias,
-           int act, const uint8_t* __restrict__ keep, float pscale, float* __restrict__ out, int64_t ldo, int64_t n,
-           int c) {
+           int act, const Drop drop, float* __restrict__ out, int64_t ldo, int64_t n, int c) {
+    const DropCtx dctx = drop_ctx(drop, stats, c);
     const int CV = (c + VEC - 1) / VEC;
     const int64_t total = n * CV, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -200,12 +265,12 @@ k_gn_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ s
         } else {
             xv[0] = x[r * ldx + col];
         }
+        float dm[VEC];
+        drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             float pre = fmaf(stats[ST_SCALE * c + col + k], xv[k] - stats[ST_AM * c + col + k], bias[col + k]);
-            float v = act_fwd(pre, act);
-            if (keep) v = keep[r * (int64_t)c + col + k] ? v * pscale : 0.f;
-            ov[k] = v;
+            ov[k] = act_fwd(pre, act) * dm[k];
         }
         if (VEC == 4) *reinterpret_cast<float4*>(out + r * ldo + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
         else out[r * ldo + col] = ov[0];
@@ -216,7 +281,8 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_gn_bwd_apply(const float* __restrict__ dout, int64_t lddo, const float* __restrict__ x, int64_t ldx,
                const float* __restrict__ stats, const float* __restrict__ bias, const float* __restrict__ coef, int act,
-               const uint8_t* __restrict__ keep, float pscale, float* __restrict__ dx, int64_t lddx, int64_t n, int c) {
+               const Drop drop, float* __restrict__ dx, int64_t lddx, int64_t n, int c) {
+    const DropCtx dctx = drop_ctx(drop, stats, c);
     const int CV = (c + VEC - 1) / VEC;
     const int64_t total = n * CV, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -231,19 +297,35 @@ k_gn_bwd_apply(const float* __restrict__ dout, int64_t lddo, const float* __rest
             xv[0] = x[r * ldx + col];
             gv[0] = dout[r * lddo + col];
         }
+        float dm[VEC];
+        drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             const int cc = col + k;
             float o = xv[k] - stats[ST_AM * c + cc];
             float pre = fmaf(stats[ST_SCALE * c + cc], o, bias[cc]);
-            float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act);
-            if (keep) u *= keep[r * (int64_t)c + cc] ? pscale : 0.f;
+            float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
             float yhat = o * stats[ST_RSTD * c + cc];
             ov[k] = fmaf(coef[0 * c + cc], u, fmaf(coef[1 * c + cc], yhat, coef[2 * c + cc]));
         }
         if (VEC == 4) *reinterpret_cast<float4*>(dx + r * lddx + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
         else dx[r * lddx + col] = ov[0];
     }
+}
+
+inline Drop make_drop(const uint8_t* keep, const unsigned long long* rng, float p) {
+    Drop d{};
+    d.pscale = 1.f;
+    if (p > 0.f) {
+        d.pscale = 1.f / (1.f - p);
+        if (keep) d.keep = keep;
+        else if (rng) {
+            d.rng = rng;
+            double t = (double)p * 4294967296.0;
+            d.thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+        }
+    }
+    return d;
 }
 
 inline int partial_ctas(int64_t n, int c, int vec) {
@@ -275,9 +357,9 @@ extern "C" size_t glass_graphnorm_workspace_bytes(int64_t n, int c) {
 }
 
 extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
-                                   const float* mean_scale, float eps, int act, const uint8_t* keep, float pscale,
-                                   float* out, int64_t ldo, float* stats, int64_t n, int c, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   const float* mean_scale, float eps, int act, const uint8_t* keep, float drop_p,
+                                   unsigned long long* rng, float* out, int64_t ldo, float* stats, int64_t n, int c,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
     GLASS_CHECK_ARG(x && weight && bias && mean_scale && out && stats && n > 0 && c > 0 && ldx >= c && ldo >= c,
                     "graphnorm_fwd: bad arguments");
     if (workspace_bytes < glass_graphnorm_workspace_bytes(n, c) || !workspace) {
@@ -290,20 +372,22 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     Fin fin{};
     fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats;
-    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
-    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, n, c, partial);
-    k_gn_finalize<false><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin);
+    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
+    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
+    GLASS_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "graphnorm_fwd: dropout p must be in [0, 1)");
+    const Drop drop = make_drop(keep, rng, drop_p);
+    k_gn_finalize<false><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, drop.rng ? rng : nullptr);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
-    if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, keep, pscale, out, ldo, n, c);
-    else k_gn_apply<1><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, keep, pscale, out, ldo, n, c);
+    if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
+    else k_gn_apply<1><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }
 
 extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* weight,
                                    const float* mean_scale, const float* stats, int act, const uint8_t* keep,
-                                   float pscale, float* dx, int64_t lddx, float* dweight, float* dbias,
+                                   float drop_p, const unsigned long long* rng, float* dx, int64_t lddx, float* dweight, float* dbias,
                                    float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
                                    void* stream) {
     GLASS_CHECK_ARG(dout && x && weight && mean_scale && stats && dx && dweight && dbias && dmean_scale && n > 0 &&
@@ -323,13 +407,14 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
     Fin fin{};
     fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
     fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale;
-    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
-    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, keep, pscale, n, c, partial);
-    k_gn_finalize<true><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin);
+    const Drop drop = make_drop(keep, rng, drop_p);
+    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
+    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
+    k_gn_finalize<true><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, nullptr);
     const int64_t work = n * (vec ? c / 4 : c);
     unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
-    if (vec) k_gn_bwd_apply<4><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, keep, pscale, dx, lddx, n, c);
-    else k_gn_bwd_apply<1><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, keep, pscale, dx, lddx, n, c);
+    if (vec) k_gn_bwd_apply<4><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
+    else k_gn_bwd_apply<1><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

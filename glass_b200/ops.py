@@ -23,7 +23,7 @@ from ._lib import ACT_ELU, ACT_NONE, ACT_RELU, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_
 
 __all__ = ["CSRAdj", "build_csr", "spmm", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
            "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",
-           "set_gemm_path", "launch_count", "reset_launch_count"]
+           "set_gemm_path", "launch_count", "reset_launch_count", "manual_seed"]
 
 # ---------------------------------------------------------------------------------------------
 # small helpers
@@ -150,31 +150,31 @@ _define("pair_linear_mix_bwd_(Tensor dout, Tensor? acts, Tensor a1, Tensor? a2, 
         "Tensor(e!) dw1, Tensor(f!) db1, Tensor(g!) workspace) -> ()", _pair_bwd_)
 
 
-def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, pscale, out, stats, workspace):
+def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, drop_p, rng, out, stats, workspace):
     lib = _lib.load()
     n, c = x.shape
     check(lib.glass_graphnorm_fwd(_p(x), x.stride(0), _p(weight), _p(bias), _p(mean_scale), eps, act, _p(keep),
-                                  pscale, _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
+                                  drop_p, _p(rng), _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
                                   workspace.numel(), _stream()), "graphnorm_fwd")
     _count(3)
 
 
 _define("graphnorm_fwd_(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, int act, Tensor? keep, "
-        "float pscale, Tensor(a!) out, Tensor(b!) stats, Tensor(c!) workspace) -> ()", _gn_fwd_)
+        "float drop_p, Tensor(d!)? rng, Tensor(a!) out, Tensor(b!) stats, Tensor(c!) workspace) -> ()", _gn_fwd_)
 
 
-def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, pscale, dx, dweight, dbias, dmean_scale, workspace):
+def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, dx, dweight, dbias, dmean_scale, workspace):
     lib = _lib.load()
     n, c = x.shape
     check(lib.glass_graphnorm_bwd(_p(dout), dout.stride(0), _p(x), x.stride(0), _p(weight), _p(mean_scale),
-                                  _p(stats), act, _p(keep), pscale, _p(dx), dx.stride(0), _p(dweight), _p(dbias),
-                                  _p(dmean_scale), n, c, _p(workspace), workspace.numel(), _stream()),
+                                  _p(stats), act, _p(keep), drop_p, _p(rng), _p(dx), dx.stride(0), _p(dweight),
+                                  _p(dbias), _p(dmean_scale), n, c, _p(workspace), workspace.numel(), _stream()),
           "graphnorm_bwd")
     _count(3)
 
 
 _define("graphnorm_bwd_(Tensor dout, Tensor x, Tensor weight, Tensor mean_scale, Tensor stats, int act, Tensor? keep, "
-        "float pscale, Tensor(a!) dx, Tensor(b!) dweight, Tensor(c!) dbias, Tensor(d!) dmean_scale, "
+        "float drop_p, Tensor? rng, Tensor(a!) dx, Tensor(b!) dweight, Tensor(c!) dbias, Tensor(d!) dmean_scale, "
         "Tensor(e!) workspace) -> ()", _gn_bwd_)
 
 
@@ -472,12 +472,34 @@ def inject_keep_masks(masks: Sequence[torch.Tensor]):
         _keep_queue = None
 
 
-def _draw_keep(n, c, p, device):
-    if _keep_queue is not None:
-        m = _keep_queue.pop(0)
-        assert m.shape == (n, c), (m.shape, (n, c))
-        return _req(m, torch.uint8, "keep", 2)
-    return torch.empty((n, c), dtype=torch.uint8, device=device).bernoulli_(1.0 - p)
+def _injected_keep(n, c):
+    """Next injected keep mask, or None when the kernels should draw the bits themselves."""
+    if _keep_queue is None:
+        return None
+    m = _keep_queue.pop(0)
+    assert m.shape == (n, c), (m.shape, (n, c))
+    return _req(m, torch.uint8, "keep", 2)
+
+
+_rng_states = {}
+
+
+def manual_seed(seed: int) -> None:
+    """Re-seed the in-kernel dropout generator of every device (counter back to 0)."""
+    for t in _rng_states.values():
+        t.copy_(torch.tensor([seed & ((1 << 63) - 1), 0], dtype=torch.int64))
+
+
+def _rng_state(device) -> torch.Tensor:
+    """{seed, call counter} of the dropout generator on `device`.  The seed is torch's current initial seed
+    (read, not drawn: torch's own random stream -- and with it the reference-identical DataLoader shuffles --
+    is left untouched), so torch.manual_seed(...) before the first training step makes runs repeatable."""
+    key = (device.type, device.index)
+    t = _rng_states.get(key)
+    if t is None:
+        seed = int(torch.initial_seed()) & ((1 << 63) - 1)
+        t = _rng_states[key] = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+    return t
 
 
 def _gn_workspace(n, c, device):
@@ -491,28 +513,30 @@ class _GraphNorm(torch.autograd.Function):
         weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
         mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
         n, c = x.shape
-        keep, pscale = None, 1.0
+        keep, rng, drop_p = None, None, 0.0
         if training and p > 0.0:
             if p >= 1.0:
                 raise RuntimeError("dropout p must be < 1")
-            keep, pscale = _draw_keep(n, c, p, x.device), 1.0 / (1.0 - p)
+            drop_p = float(p)
+            keep = _injected_keep(n, c)
+            rng = None if keep is not None else _rng_state(x.device)
         out = torch.empty((n, c), dtype=torch.float32, device=x.device)
-        stats = torch.empty((5, c), dtype=torch.float32, device=x.device)
-        _ops.graphnorm_fwd_(x, weight, bias, mean_scale, float(eps), act, keep, pscale, out, stats,
+        stats = torch.empty((6, c), dtype=torch.float32, device=x.device)
+        _ops.graphnorm_fwd_(x, weight, bias, mean_scale, float(eps), act, keep, drop_p, rng, out, stats,
                             _gn_workspace(n, c, x.device))
-        ctx.save_for_backward(x, weight, mean_scale, stats, keep)
-        ctx.cfg = (act, pscale)
+        ctx.save_for_backward(x, weight, mean_scale, stats, keep, rng)
+        ctx.cfg = (act, drop_p)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, mean_scale, stats, keep = ctx.saved_tensors
-        act, pscale = ctx.cfg
+        x, weight, mean_scale, stats, keep, rng = ctx.saved_tensors
+        act, drop_p = ctx.cfg
         dout, _ = _rowmajor(dout)
         n, c = x.shape
         dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
         dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
-        _ops.graphnorm_bwd_(dout, x, weight, mean_scale, stats, act, keep, pscale, dx, dw, db, da,
+        _ops.graphnorm_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, dx, dw, db, da,
                             _gn_workspace(n, c, x.device))
         return dx, dw, db, da, None, None, None, None
 
@@ -541,9 +565,9 @@ class _GraphNormCat(torch.autograd.Function):
         out = torch.empty((n, d), dtype=torch.float32, device=xs[0].device)
         stats, off = [], 0
         for t, w in zip(xs, widths):
-            st = torch.empty((5, w), dtype=torch.float32, device=t.device)
+            st = torch.empty((6, w), dtype=torch.float32, device=t.device)
             _ops.graphnorm_fwd_(t, weight[off:off + w], bias[off:off + w], mean_scale[off:off + w], float(eps),
-                                ACT_NONE, None, 1.0, out[:, off:off + w], st, _gn_workspace(n, w, t.device))
+                                ACT_NONE, None, 0.0, None, out[:, off:off + w], st, _gn_workspace(n, w, t.device))
             stats.append(st)
             off += w
         ctx.save_for_backward(weight, mean_scale, *xs, *stats)
@@ -563,7 +587,7 @@ class _GraphNormCat(torch.autograd.Function):
         for t, st, w in zip(xs, stats, widths):
             dx = torch.empty((n, w), dtype=torch.float32, device=t.device)
             _ops.graphnorm_bwd_(dout[:, off:off + w], t, weight[off:off + w], mean_scale[off:off + w], st, ACT_NONE,
-                                None, 1.0, dx, dw[off:off + w], db[off:off + w], da[off:off + w],
+                                None, 0.0, None, dx, dw[off:off + w], db[off:off + w], da[off:off + w],
                                 _gn_workspace(n, w, t.device))
             dxs.append(dx)
             off += w

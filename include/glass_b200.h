@@ -124,21 +124,24 @@ int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts
  * 249, 257, 266), optionally followed by the activation and dropout that the reference applies
  * right after it (impl/models.py:166, 251, 258-259).
  *   mu = mean_rows(x); o = x - mean_scale*mu; var = mean_rows(o^2); rstd = 1/sqrt(var+eps)
- *   out = keep * pscale * act(weight*o*rstd + bias)
- * stats [5, c]: rows = scale (weight*rstd), am (mean_scale*mu), mu, rstd, bias -- written by fwd,
- * consumed by bwd.  keep: uint8 [n,c] (ld c) or NULL; pscale = 1/(1-p).
+ *   out = keep/(1-p) * act(weight*o*rstd + bias)
+ * stats [6, c]: rows = scale (weight*rstd), am (mean_scale*mu), mu, rstd, bias, dropout call id -- written
+ * by fwd, consumed by bwd.  Dropout (drop_p > 0): `keep` uint8 [n,c] (ld c) is an explicit mask; with
+ * keep == NULL and rng != NULL the kernels generate the bits themselves (Philox4x32-10 keyed by rng[0],
+ * counter = element index and a per-call id taken from rng[1], which fwd increments) and bwd regenerates
+ * them from the id saved in `stats`; with both NULL there is no dropout.
  * Column sums are accumulated in fp64 per block and reduced in block order (deterministic).
  * workspace: glass_graphnorm_workspace_bytes(n, c).
  * ------------------------------------------------------------------------------------------ */
 size_t glass_graphnorm_workspace_bytes(int64_t n, int c);
 int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
-                        const float* mean_scale, float eps, int act, const uint8_t* keep, float pscale,
-                        float* out, int64_t ldo, float* stats, int64_t n, int c, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        const float* mean_scale, float eps, int act, const uint8_t* keep, float drop_p,
+                        unsigned long long* rng, float* out, int64_t ldo, float* stats, int64_t n, int c,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* dx [n,c]; dweight, dbias, dmean_scale [c] are OVERWRITTEN (not accumulated). */
 int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* weight,
                         const float* mean_scale, const float* stats, int act, const uint8_t* keep,
-                        float pscale, float* dx, int64_t lddx, float* dweight, float* dbias,
+                        float drop_p, const unsigned long long* rng, float* dx, int64_t lddx, float* dweight, float* dbias,
                         float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
                         void* stream);
 

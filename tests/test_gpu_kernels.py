@@ -249,16 +249,37 @@ def test_graph_norm_fwd_bwd(n, c, act, p):
         assert rel_err(d.grad.cpu(), cc.grad) < TOL, name
 
 
-def test_graph_norm_dropout_draws_masks():
+def test_graph_norm_dropout_in_kernel_generator():
+    """Philox bits generated inside the kernels: right drop rate, survivors scaled by 1/(1-p), a fresh mask
+    per call, and backward regenerates exactly the mask forward used (checked against the injected-mask path)."""
     from glass_b200 import ops
-    x = torch.randn(4000, 64, device=DEV)
-    w, b, a = torch.ones(64, device=DEV), torch.zeros(64, device=DEV), torch.ones(64, device=DEV)
-    out = ops.graph_norm(x, w, b, a, 1e-5, 0, 0.5, True)
-    frac = float((out == 0).float().mean())
-    assert 0.47 < frac < 0.53
-    ev = ops.graph_norm(x, w, b, a, 1e-5, 0, 0.5, False)
-    kept = out != 0
-    assert rel_err(out[kept], 2 * ev[kept]) < 1e-6
+    g = torch.Generator().manual_seed(0)
+    for n, c, act, p in ((4000, 64, 0, 0.5), (777, 17, 2, 0.3)):
+        x = (torch.randn(n, c, generator=g) + 0.1).to(DEV)
+        w, b, a = (torch.rand(c, generator=g) + 0.5).to(DEV), torch.randn(c, generator=g).to(DEV), torch.ones(c, device=DEV)
+        ev = ops.graph_norm(x, w, b, a, 1e-5, act, p, False)
+        xs = [x.clone().requires_grad_(True) for _ in range(2)]
+        ws = [w.clone().requires_grad_(True) for _ in range(2)]
+        out = ops.graph_norm(xs[0], ws[0], b, a, 1e-5, act, p, True)
+        out2 = ops.graph_norm(x, w, b, a, 1e-5, act, p, True)
+        keep = (out != 0) | (ev == 0)
+        frac = float((~keep).float().mean())
+        assert abs(frac - p) < 0.02, frac
+        assert rel_err(out[keep].detach(), ev[keep] / (1 - p)) < 1e-6
+        assert not torch.equal(out2 != 0, out != 0)                      # next call, next mask
+        gout = torch.randn(n, c, generator=g).to(DEV)
+        out.backward(gout)
+        with ops.inject_keep_masks([keep.to(torch.uint8)]):
+            ref = ops.graph_norm(xs[1], ws[1], b, a, 1e-5, act, p, True)
+        assert torch.equal(ref, out)
+        ref.backward(gout)
+        assert rel_err(xs[0].grad, xs[1].grad) < 1e-6 and rel_err(ws[0].grad, ws[1].grad) < 1e-6
+    # re-seeding repeats the sequence
+    ops.manual_seed(123)
+    m1 = ops.graph_norm(x, w, b, a, 1e-5, 0, 0.5, True) != 0
+    ops.manual_seed(123)
+    m2 = ops.graph_norm(x, w, b, a, 1e-5, 0, 0.5, True) != 0
+    assert torch.equal(m1, m2)
 
 
 def test_graph_norm_cat_matches_norm_of_concat():
