@@ -50,6 +50,8 @@ PROTOTYPES = {
     "glass_segment_pool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "glass_segment_pool_batch_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
     "glass_segment_pool_batch_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "glass_adam_chunk": (_i32, []),
+    "glass_adam_step": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _f32, _f32, _f32, _f32, _vp]),
     "glass_maxzoz": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "glass_label_mask": (_i32, [_vp, _vp, _i64, _vp]),
     "glass_pad2batch": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

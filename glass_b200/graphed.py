@@ -67,9 +67,9 @@ class GraphedTrainStep:
         # pass); with several ranks GradAverager averages them with two NCCL all-reduces (table + the rest).
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.averager = GradAverager(self.params, group) if self.world > 1 else None
-        self.lr = torch.tensor(float(lr), device=dev)
-        self.opt = torch.optim.Adam(model.parameters(), lr=self.lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                                    capturable=True, fused=True)
+        from .optim import FusedAdam
+        self.opt = FusedAdam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.lr = self.opt.lr
         self.loss = torch.zeros((), device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         model.train()
@@ -107,10 +107,7 @@ class GraphedTrainStep:
             own = self.model.state_dict()
             for k, v in state_dict.items():
                 own[k].copy_(v)
-            for st in self.opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            self.opt.reset_state()
 
     def set_lr(self, lr: float):
         self.lr.fill_(float(lr))

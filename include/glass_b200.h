@@ -189,6 +189,18 @@ int glass_label_mask(const int64_t* z, uint8_t* mask, int64_t n_node, void* stre
 int glass_pad2batch(const int64_t* pad, int64_t b, int64_t lmax, int64_t* batch_out, int64_t* pos_out,
                     int64_t* n_valid, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-tensor Adam in one launch (optimizer of GLASSTest.py:213 for the captured train step; same update
+ * as torch.optim.Adam without amsgrad).  table: n_tensors rows {float* p, const float* g, float* m, float* v,
+ * int64 n} in device memory; the host splits every tensor into chunks of glass_adam_chunk() elements and
+ * passes, per chunk, the tensor index and the first element.  lr: 1 float and state: 2 floats {step count, 0}
+ * in device memory (the kernel advances the step count, so a captured graph can be replayed).
+ * ------------------------------------------------------------------------------------------ */
+int glass_adam_chunk(void);
+int glass_adam_step(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_begin, int64_t n_chunks,
+                    const float* lr, float* state, float beta1, float beta2, float eps, float weight_decay,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
