@@ -58,7 +58,9 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
-        """Parameters without a gradient this step are skipped (like torch).  The pointer table is rebuilt on
+        """Parameters without a gradient this step are skipped (like torch; the step count used for the bias
+        correction is global here, per parameter in torch -- identical as long as every parameter receives a
+        gradient every step, which is the case for the GLASS model).  The pointer table is rebuilt on
         every eager call; inside a CUDA-graph capture the (static) addresses are baked into the graph through a
         pinned staging copy."""
         rows = []

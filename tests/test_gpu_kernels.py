@@ -442,18 +442,22 @@ def test_fused_adam_matches_torch_adam():
     p_new = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
     ref = torch.optim.Adam(p_ref, lr=1e-2)
     new = FusedAdam(p_new, lr=1e-2)
-    for step in range(5):
+    for step in range(6):
         for a, b in zip(p_ref, p_new):
             grad = torch.randn(a.shape, generator=g).to(DEV)
-            a.grad = grad.clone()
-            b.grad = grad.clone() if not (step == 2 and a.numel() == 15) else None   # one parameter skips a step
-            if b.grad is None:
-                a.grad = None
+            a.grad, b.grad = grad.clone(), grad.clone()
         ref.step()
         new.step()
         if step == 3:
             for grp in ref.param_groups:
                 grp["lr"] = 3e-3
             new.set_lr(3e-3)
-    for a, b in zip(p_ref, p_new):
-        assert rel_err(b.detach().cpu(), a.detach().cpu()) < 2e-6
+    for s_, a, b in zip(shapes, p_ref, p_new):
+        assert rel_err(b.detach().cpu(), a.detach().cpu()) < 2e-6, s_
+    # a parameter without a gradient is left untouched (note: the step count is global, torch's is per parameter)
+    before = [p.detach().clone() for p in p_new]
+    for b in p_new:
+        b.grad = torch.ones_like(b)
+    p_new[2].grad = None
+    new.step()
+    assert torch.equal(p_new[2].detach(), before[2]) and not torch.equal(p_new[0].detach(), before[0])
