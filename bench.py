@@ -318,8 +318,8 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="glass_b200", choices=["glass_b200", "reference"])
     ap.add_argument("--workload", default="em_user_shaped")
     ap.add_argument("--cpu-steps", type=int, default=3)
