@@ -111,23 +111,33 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU port (reference arm)
-def cpu_port_steps(wl, n_steps: int, warmup: int, train: bool = True):
-    """Times the oracle port of the reference modules (same ATen op sequence as impl/models.py on CPU)."""
+def cpu_port_steps(wl, n_steps: int, warmup: int, train: bool = True, device=None):
+    """Times the oracle port of the reference modules (same ATen op sequence as impl/models.py).  On the CPU
+    this is the `cpu_baseline` / `--impl reference` arm; with a CUDA `device` it is the reference's own eager
+    torch.sparse path on the GPU (reported only as an extra, `--gpu-eager-baseline`)."""
     from oracle import glass_oracle as O
     p = wl["params"]
     g = wl["g"]
     cfg = O.GlassConfig(hidden_dim=p["hidden_dim"], conv_layer=p["conv_layer"], aggr=p["aggr"], z_ratio=p["z_ratio"],
                         dropout=p["dropout"], pool=p["pool"], jk=True, activation="elu", out_dim=wl["out_dim"])
     sd = O.init_state_dict(cfg, wl["max_deg"] + 1, seed=0, pretrained=wl["table"])
+    if device is not None:
+        sd = {k: v.to(device) for k, v in sd.items()}
     model = O.OracleModel(cfg, sd)
     opt = torch.optim.Adam(model.params, lr=p["lr"])
     loss_fn = O.loss_fn_for(wl["out_dim"] == 1 and g.y.dtype == torch.float32)
-    batches = batches_for(wl, n_steps + warmup, 0, 1)
+    mv = (lambda t: t.to(device)) if device is not None else (lambda t: t)
+    gx, gei, gea = mv(g.x), mv(g.edge_index), mv(g.edge_attr)
+    batches = [(mv(a), mv(b)) for a, b in batches_for(wl, n_steps + warmup, 0, 1)]
     for pos, y in batches[:warmup]:
-        model.step(opt, g.x, g.edge_index, g.edge_attr, pos, y, loss_fn, training=train)
+        model.step(opt, gx, gei, gea, pos, y, loss_fn, training=train)
+    if device is not None:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for pos, y in batches[warmup:]:
-        model.step(opt, g.x, g.edge_index, g.edge_attr, pos, y, loss_fn, training=train)
+        model.step(opt, gx, gei, gea, pos, y, loss_fn, training=train)
+    if device is not None:
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return p["batch_size"] * n_steps / dt, dt / n_steps
 
@@ -304,6 +314,11 @@ def run_product(args):
                                     "sample": f"{args.cpu_steps} train steps (after 1 warm-up) of batch {bs} on the full "
                                               f"{wl['name']} graph, oracle port of impl/models.py",
                                     "ms_per_step": per * 1e3}
+        if world == 1 and args.gpu_eager_baseline:
+            v, per = cpu_port_steps(wl, 20, 3, device=dev)
+            line["gpu_eager_baseline"] = {"value": v, "unit": "subgraphs/s", "ms_per_step": per * 1e3,
+                                          "what": "oracle port of impl/models.py run eagerly on this GPU "
+                                                  "(torch.sparse COO @ dense -> cuSPARSE, ATen element-wise, torch Adam)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels are still alive; tearing the communicator down under them
@@ -325,6 +340,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the reference's eager torch.sparse op sequence on this GPU (extra key)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

@@ -13,7 +13,8 @@ reference file:line it follows.  It deliberately executes the same ATen op
 sequence as the reference (sparse-COO @ dense, `mean[batch]` gathers, two
 Linear calls + torch.where) so that timing it on host cores is a faithful CPU
 baseline ("port") when /root/reference is not present (it is absent on the GPU
-box).
+box).  Every function follows its inputs' device, so the same op sequence can also be timed as the "eager
+torch.sparse on the GPU" baseline (bench.py --gpu-eager-baseline); the parity tests always run it on the CPU.
 
 Pinning: the reference has no tests or golden vectors for this path
 (SURVEY.md section 4).  The oracle is pinned instead against outputs of the
@@ -47,7 +48,7 @@ def pad2batch(pad: torch.Tensor):
 
 def max_zero_one(n_node: int, pos: torch.Tensor) -> torch.Tensor:
     """impl/utils.py:32-45 (MaxZOZ) -- z[n] = 1 iff node n occurs in any row of pos; int64 [N]."""
-    z = torch.zeros(n_node, dtype=torch.int64)
+    z = torch.zeros(n_node, dtype=torch.int64, device=pos.device)
     flat = pos.flatten()
     z[flat[flat >= 0]] = 1
     return z
@@ -139,16 +140,17 @@ def graph_norm(x, weight, bias, mean_scale, eps: float = 1e-5):
     Same op sequence as PyG: scatter_mean -> mean[batch] gather -> centred var -> affine.
     """
     n = x.shape[0]
-    batch = torch.zeros(n, dtype=torch.long)
-    mean = torch.zeros(1, x.shape[1], dtype=x.dtype).index_add_(0, batch, x) / n
+    batch = torch.zeros(n, dtype=torch.long, device=x.device)
+    mean = torch.zeros(1, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, batch, x) / n
     out = x - mean[batch] * mean_scale
-    var = torch.zeros(1, x.shape[1], dtype=x.dtype).index_add_(0, batch, out * out) / n
+    var = torch.zeros(1, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, batch, out * out) / n
     std = (var + eps).sqrt()[batch]
     return weight * out / std + bias
 
 
 def _segment_count(batch, n_seg, dtype):
-    return torch.zeros(n_seg, dtype=dtype).index_add_(0, batch, torch.ones(batch.shape[0], dtype=dtype))
+    return torch.zeros(n_seg, dtype=dtype, device=batch.device).index_add_(
+        0, batch, torch.ones(batch.shape[0], dtype=dtype, device=batch.device))
 
 
 def pool_nodes(x, batch, kind: str, n_seg: Optional[int] = None):
@@ -159,13 +161,13 @@ def pool_nodes(x, batch, kind: str, n_seg: Optional[int] = None):
         x = x * cnt.pow(-0.5)[batch].view(-1, 1)
         kind = "sum"
     if kind == "sum":
-        return torch.zeros(n_seg, x.shape[1], dtype=x.dtype).index_add_(0, batch, x)
+        return torch.zeros(n_seg, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, batch, x)
     if kind == "mean":
         cnt = _segment_count(batch, n_seg, x.dtype).clamp(min=1)
-        return torch.zeros(n_seg, x.shape[1], dtype=x.dtype).index_add_(0, batch, x) / cnt.view(-1, 1)
+        return torch.zeros(n_seg, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, batch, x) / cnt.view(-1, 1)
     if kind == "max":
         idx = batch.view(-1, 1).expand_as(x)
-        return torch.zeros(n_seg, x.shape[1], dtype=x.dtype).scatter_reduce(
+        return torch.zeros(n_seg, x.shape[1], dtype=x.dtype, device=x.device).scatter_reduce(
             0, idx, x, reduce="amax", include_self=False)
     raise NotImplementedError  # GLASSTest.py:171
 
@@ -235,7 +237,7 @@ def emb_zg_conv(sd, x_ids, adj, z, cfg: GlassConfig, training: bool,
     nxt = (lambda: keeps.pop(0)) if keeps is not None else (lambda: None)
     n = x_ids.shape[0]
     if z is None:
-        mask = torch.ones(n, 1, dtype=torch.bool)                        # :242-244
+        mask = torch.ones(n, 1, dtype=torch.bool, device=x_ids.device)   # :242-244
     else:
         mask = (z > 0.5).reshape(-1, 1)                                  # :246
     act = _ACTS[cfg.activation]
