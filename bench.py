@@ -220,7 +220,7 @@ def run_product(args):
 
     from glass_b200 import build as _build
     _build.build()
-    from glass_b200 import ops, run, train, utils
+    from glass_b200 import ops, run
     from glass_b200.graphed import GraphedTrainStep, train_epoch
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))

@@ -9,7 +9,9 @@
 // result is deterministic and matches a sequential CPU loop over the sorted entries.
 //
 // Roofline: compulsory HBM bytes = 4(N+1) + 8 nnz + 8 N H.  The gathers
-// (4 H nnz bytes) are served by L1/L2: X (14.7 MB at the em_user shape) is L2-resident.
+// (4 H nnz bytes) are served by L1/L2: X (14.7 MB at the em_user shape) is L2-resident.  Measured tuning
+// (em_user shape): 5 resident CTAs per SM (48 registers) 131 us; 3 / 6 / 8 CTAs 141 / 143 / 150 us; deeper
+// unrolling with fewer CTAs 205-225 us; L1::no_allocate gathers 156 us.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -29,15 +31,6 @@ struct Vec<4> {
     using T = float4;
     static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
     static __device__ __forceinline__ T load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-    // gather that does not allocate in L1.  Measured SLOWER (156 vs 131 us at the em_user shape) although the L1
-    // hit rate is only ~4 %: kept for experiments, not used by the dispatcher.
-    static __device__ __forceinline__ T load_na(const float* p) {
-        float4 r;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                     : "l"(p));
-        return r;
-    }
     static __device__ __forceinline__ void store(float* p, const T& v) { *reinterpret_cast<float4*>(p) = v; }
     static __device__ __forceinline__ void fma(T& a, float s, const T& x) {
         a.x = fmaf(s, x.x, a.x);
@@ -51,7 +44,6 @@ struct Vec<1> {
     using T = float;
     static __device__ __forceinline__ T zero() { return 0.f; }
     static __device__ __forceinline__ T load(const float* p) { return __ldg(p); }
-    static __device__ __forceinline__ T load_na(const float* p) { return __ldg(p); }
     static __device__ __forceinline__ void store(float* p, const T& v) { *p = v; }
     static __device__ __forceinline__ void fma(T& a, float s, const T& x) { a = fmaf(s, x, a); }
 };
@@ -87,7 +79,7 @@ struct PlanWork {
 
 // G lanes per row, VEC floats per lane and chunk, KCH column chunks per lane (h <= G*VEC*KCH).
 // EXACT: h == G*VEC*KCH (no column guards).  IDX32: every element offset into x fits 32 bits.
-template <int G, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, class Work, bool NA = false>
+template <int G, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, class Work>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const int32_t* __restrict__ col,
                                                          const float* __restrict__ val, const float* __restrict__ x,
                                                          int64_t ldx, int64_t n_items, int h) {
@@ -141,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
                 const float w = __int_as_float(cv.y);
 #pragma unroll
                 for (int k = 0; k < KCH; ++k)
-                    if (colok[k]) V::fma(acc[k], w, NA ? V::load_na(xr + coff[k]) : V::load(xr + coff[k]));
+                    if (colok[k]) V::fma(acc[k], w, V::load(xr + coff[k]));
             }
         }
 #pragma unroll
@@ -171,7 +163,7 @@ struct Plan {   // host view of the arguments of glass_spmm_csr_planned
     float* scratch;
 };
 
-template <int G, int VEC, int KCH, int MINB = 4, bool NA = false>
+template <int G, int VEC, int KCH, int MINB = 4>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
            int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
     const int64_t n_items = plan ? plan->n_items : n_rows;
@@ -186,10 +178,10 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* val, const fl
     do {                                                                                                              \
         if (plan) {                                                                                                   \
             PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h};          \
-            k_spmm<G, VEC, KCH, E, I, MINB, PlanWork, NA><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);    \
+            k_spmm<G, VEC, KCH, E, I, MINB, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);    \
         } else {                                                                                                      \
             RowWork w{rowptr, y, ldy};                                                                                \
-            k_spmm<G, VEC, KCH, E, I, MINB, RowWork, NA><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);     \
+            k_spmm<G, VEC, KCH, E, I, MINB, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);     \
         }                                                                                                             \
     } while (0)
     if (exact && idx32) GLASS_SPMM_GO(true, true);

@@ -94,8 +94,9 @@ class GraphedTrainStep:
         self.loss.copy_(loss.detach())
 
     def capture(self):
-        """Capture after restoring nothing: the warm-up steps DID update the parameters; callers that need
-        an untouched model should snapshot/restore the state_dict around construction (see reset_to)."""
+        """Capture one training step.  NOTE: the warm-up steps in __init__ already updated the parameters and
+        the Adam state; callers that need the pre-warm-up model snapshot its state_dict before constructing
+        this object and call reset_to(snapshot) after capture()."""
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step_eager()

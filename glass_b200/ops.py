@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_ELU, ACT_NONE, ACT_RELU, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
+from ._lib import ACT_NONE, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
 
 __all__ = ["CSRAdj", "build_csr", "spmm", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
            "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",

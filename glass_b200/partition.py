@@ -15,7 +15,7 @@ layout.  GEMMs, label mix, pooling gathers are row-local and need no communicati
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist

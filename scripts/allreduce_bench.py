@@ -1,5 +1,5 @@
 """torchrun --nproc-per-node P scripts/allreduce_bench.py : NCCL vs symmetric-memory all-reduce of the DP gradient buffer."""
-import os, sys, time
+import os, sys
 import torch, torch.distributed as dist
 import torch.distributed._symmetric_memory as sm
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

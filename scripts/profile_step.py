@@ -3,7 +3,7 @@ import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from glass_b200 import run, ops
+from glass_b200 import run
 from glass_b200.graphed import GraphedTrainStep
 torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 wl = bench.make_workload(sys.argv[1] if len(sys.argv) > 1 else "em_user_shaped")

@@ -46,7 +46,6 @@ for cfg in [(128, 32, 0, 8, 0, 0.8), (128, 32, 0, 64, 0, 0.8), (128, 64, 0, 64, 
         print(cfg, "EXC", type(e).__name__, e, flush=True)
 
 # timing at the em_user shape
-import time
 for (n, k1, k2, h, act) in [(57333, 64, 0, 64, 2), (57333, 64, 64, 64, 0)]:
     g = torch.Generator().manual_seed(0)
     a1 = torch.randn(n, k1, generator=g).to(dev); a2 = torch.randn(n, k2, generator=g).to(dev) if k2 else None
