@@ -231,19 +231,36 @@ __global__ void __launch_bounds__(kThreads) k_pair_bwd_dw(DPSrc P, ASrc A, float
     }
 }
 
-__global__ void k_pair_bwd_dw_reduce(const float* __restrict__ part, int splits, int h, int K, float* __restrict__ dw0,
-                                     float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1) {
+// 512 threads = 32 output elements x 16 split lanes; lane q adds splits q, q+16, ... in order, then the 16
+// lane sums are added in lane order (deterministic).  A serial loop over up to 296 splits per output was
+// latency bound (21 us at component's H = 17).
+constexpr int kRedLanes = 16;
+__global__ void __launch_bounds__(32 * kRedLanes) k_pair_bwd_dw_reduce(const float* __restrict__ part, int splits,
+                                                                      int h, int K, float* __restrict__ dw0,
+                                                                      float* __restrict__ db0, float* __restrict__ dw1,
+                                                                      float* __restrict__ db1) {
+    __shared__ float sm[kRedLanes][33];
     const int J = 2 * h;
-    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= (int64_t)J * (K + 1)) return;
-    int j = (int)(e / (K + 1)), k = (int)(e % (K + 1));
+    const int el = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int64_t total = (int64_t)J * (K + 1);
+    const int64_t e = blockIdx.x * 32ll + el;
+    const bool ok = e < total;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * J * (K + 1) + e];  // fixed order
-    float* dw = j < h ? dw0 : dw1;
-    float* db = j < h ? db0 : db1;
-    int jr = j < h ? j : j - h;
-    if (k < K) dw[(int64_t)jr * K + k] = s;
-    else db[jr] = s;
+    if (ok) {
+#pragma unroll 4
+        for (int sp = q; sp < splits; sp += kRedLanes) s += part[(int64_t)sp * total + e];
+    }
+    sm[q][el] = s;
+    __syncthreads();
+    if (q == 0 && ok) {
+        float t = sm[0][el];
+#pragma unroll
+        for (int i = 1; i < kRedLanes; ++i) t += sm[i][el];
+        const int j = (int)(e / (K + 1)), k = (int)(e % (K + 1));
+        const int jr = j < h ? j : j - h;
+        if (k < K) (j < h ? dw0 : dw1)[(int64_t)jr * K + k] = t;
+        else (j < h ? db0 : db1)[jr] = t;
+    }
 }
 
 }  // namespace
@@ -252,7 +269,7 @@ __global__ void k_pair_bwd_dw_reduce(const float* __restrict__ part, int splits,
 int dw_splits(int64_t n, int h, int k) {
     int64_t tiles = ceil_div(2 * (int64_t)h, BM) * ceil_div(k, BN);
     int64_t s = ceil_div(2 * 148, tiles);
-    int64_t max_s = ceil_div(n, 4 * BK);
+    int64_t max_s = ceil_div(n, BK);   // small graphs: one BK-row pass per CTA, the whole kernel is one load round
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
     return (int)s;
@@ -287,7 +304,7 @@ int pair_bwd_simt(const float* dout, int64_t lddo, const float* acts, const floa
     k_pair_bwd_dw<<<grid, kThreads, 0, st>>>(P, A, part, n, rows_per_split);
     GLASS_LAUNCH_CHECK();
     int64_t total = 2 * (int64_t)h * (K + 1);
-    k_pair_bwd_dw_reduce<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, splits, h, K, dw0, db0, dw1, db1);
+    k_pair_bwd_dw_reduce<<<(unsigned)ceil_div(total, 32), 32 * kRedLanes, 0, st>>>(part, splits, h, K, dw0, db0, dw1, db1);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

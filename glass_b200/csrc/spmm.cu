@@ -3,10 +3,11 @@
 //
 // Mapping: a sub-warp GROUP of G lanes owns one CSR row; lane l of the group owns VEC consecutive
 // feature columns (VEC = 4 -> one 16-byte gather per neighbour and lane, a whole 256-byte feature row
-// per 16 lanes at H = 64).  The group streams its (col, val) entries G at a time with one coalesced
-// load per array, broadcasts them with width-G shuffles, and issues UNROLL independent float4 gathers
-// before the dependent FMA chain.  Accumulation is a single fp32 chain per column in CSR order, so the
-// result is deterministic and matches a sequential CPU loop over the sorted entries.
+// per 16 lanes at H = 64).  The group streams its (col, val) entries one per lane at a time with one
+// coalesced load per array, stages them in a warp-private shared-memory slot, and issues 4 independent
+// float4 gathers before the dependent FMA chain.  In the throughput configuration accumulation is a
+// single fp32 chain per column in CSR order: deterministic, equal to a sequential CPU loop over the
+// sorted entries.  Small graphs use extra lanes across the neighbours of a row (see k_spmm).
 //
 // Roofline: compulsory HBM bytes = 4(N+1) + 8 nnz + 8 N H.  The gathers
 // (4 H nnz bytes) are served by L1/L2: X (14.7 MB at the em_user shape) is L2-resident.  Measured tuning
@@ -38,6 +39,12 @@ struct Vec<4> {
         a.z = fmaf(s, x.z, a.z);
         a.w = fmaf(s, x.w, a.w);
     }
+    static __device__ __forceinline__ void add_xor(T& a, unsigned mask, int off) {
+        a.x += __shfl_xor_sync(mask, a.x, off);
+        a.y += __shfl_xor_sync(mask, a.y, off);
+        a.z += __shfl_xor_sync(mask, a.z, off);
+        a.w += __shfl_xor_sync(mask, a.w, off);
+    }
 };
 template <>
 struct Vec<1> {
@@ -46,6 +53,7 @@ struct Vec<1> {
     static __device__ __forceinline__ T load(const float* p) { return __ldg(p); }
     static __device__ __forceinline__ void store(float* p, const T& v) { *p = v; }
     static __device__ __forceinline__ void fma(T& a, float s, const T& x) { a = fmaf(s, x, a); }
+    static __device__ __forceinline__ void add_xor(T& a, unsigned mask, int off) { a += __shfl_xor_sync(mask, a, off); }
 };
 
 // Work description: either one item per CSR row, or a precomputed plan in which rows longer than
@@ -77,21 +85,30 @@ struct PlanWork {
     }
 };
 
-// G lanes per row, VEC floats per lane and chunk, KCH column chunks per lane (h <= G*VEC*KCH).
+// A row group is G x S lanes: lane l of G owns VEC consecutive feature columns per chunk (KCH column
+// chunks, h <= G*VEC*KCH), slot s of S takes every S-th stored entry of the row; the S partial sums are
+// added by a butterfly at the end of the row (fixed order -> deterministic).  S = 1 is the throughput
+// configuration (one sequential fp32 chain per output, exactly the CPU loop order); S = 32/G is used
+// for graphs that do not fill the machine, where the longest row's dependent gather chain is the
+// whole kernel time (density: 409-entry row on 2 lanes = 65 us; 16 slots -> see DESIGN.md 4.1).
 // EXACT: h == G*VEC*KCH (no column guards).  IDX32: every element offset into x fits 32 bits.
-template <int G, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, class Work>
+template <int G, int S, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, class Work>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const int32_t* __restrict__ col,
                                                          const float* __restrict__ val, const float* __restrict__ x,
                                                          int64_t ldx, int64_t n_items, int h) {
     using V = Vec<VEC>;
+    constexpr int GW = G * S;                          // lanes per row
+    static_assert(GW <= 32 && (GW & (GW - 1)) == 0, "row group must be a power-of-two part of a warp");
     // (col, val) staging: one 8-byte slot per lane, double buffered so that one __syncwarp per chunk suffices
     __shared__ int2 s_e[2][kThreads];
     const int lane = threadIdx.x & 31;
-    const int l = lane & (G - 1);                      // lane inside the group
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    const int gbase = threadIdx.x & ~(G - 1);
-    const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / G);
-    int64_t item = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+    const int lg = lane & (GW - 1);                    // lane inside the row group
+    const int l = lg & (G - 1);                        // feature lane
+    const int slot = lg / G;                           // neighbour slot
+    const unsigned gmask = (GW == 32) ? 0xffffffffu : (((1u << GW) - 1u) << (lane & ~(GW - 1)));
+    const int gbase = threadIdx.x & ~(GW - 1);
+    const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / GW);
+    int64_t item = (int64_t)blockIdx.x * (kThreads / GW) + threadIdx.x / GW;
     const uint32_t ldx32 = (uint32_t)ldx;
 
     bool colok[KCH];
@@ -113,21 +130,21 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
         // software pipeline: the (col, val) pair of the NEXT chunk is in flight while this chunk is gathered
         int nc = 0;
         float nv = 0.f;
-        if (e_begin + l < e_end) {
-            nc = __ldg(col + e_begin + l);
-            nv = __ldg(val + e_begin + l);
+        if (e_begin + lg < e_end) {
+            nc = __ldg(col + e_begin + lg);
+            nv = __ldg(val + e_begin + lg);
         }
-        for (int32_t e0 = e_begin; e0 < e_end; e0 += G, buf ^= 1) {
-            const int cnt = min(G, e_end - e0);
+        for (int32_t e0 = e_begin; e0 < e_end; e0 += GW, buf ^= 1) {
+            const int cnt = min(GW, e_end - e0);
             s_e[buf][threadIdx.x] = make_int2(nc, __float_as_int(nv));
-            if (e0 + G + l < e_end) {
-                nc = __ldg(col + e0 + G + l);
-                nv = __ldg(val + e0 + G + l);
+            if (e0 + GW + lg < e_end) {
+                nc = __ldg(col + e0 + GW + lg);
+                nv = __ldg(val + e0 + GW + lg);
             }
             __syncwarp(gmask);
             const int2* se = &s_e[buf][gbase];
 #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
+            for (int j = slot; j < cnt; j += S) {
                 const int2 cv = se[j];                                  // broadcast read inside the group
                 const float* xr = IDX32 ? x + (uint32_t)cv.x * ldx32 : x + (int64_t)cv.x * ldx;
                 const float w = __int_as_float(cv.y);
@@ -136,9 +153,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
                     if (colok[k]) V::fma(acc[k], w, V::load(xr + coff[k]));
             }
         }
+        if (S > 1) {
 #pragma unroll
-        for (int k = 0; k < KCH; ++k)
-            if (colok[k]) V::store(yr + coff[k], acc[k]);
+            for (int off = G; off < GW; off <<= 1)
+#pragma unroll
+                for (int k = 0; k < KCH; ++k) V::add_xor(acc[k], gmask, off);
+        }
+        if (S == 1 || slot == 0) {
+#pragma unroll
+            for (int k = 0; k < KCH; ++k)
+                if (colok[k]) V::store(yr + coff[k], acc[k]);
+        }
     }
 }
 
@@ -163,11 +188,22 @@ struct Plan {   // host view of the arguments of glass_spmm_csr_planned
     float* scratch;
 };
 
-template <int G, int VEC, int KCH, int MINB = 4>
+// Lanes of one full-occupancy wave (148 SMs x 2048 threads on B200): below about two of them the kernel is
+// bound by its longest row, not by gather throughput, and the neighbour-parallel configuration wins.
+static bool latency_regime(int64_t n_items) {
+    static const int force = [] {
+        const char* e = getenv("GLASS_B200_SPMM_SLOTS");   // 0: never, 1: always, unset: by size
+        return e ? atoi(e) : -1;
+    }();
+    if (force >= 0) return force != 0;
+    return n_items * 32 <= 2ll * sm_count() * 2048;
+}
+
+template <int G, int S, int VEC, int KCH, int MINB = 4>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
            int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
     const int64_t n_items = plan ? plan->n_items : n_rows;
-    const int64_t groups_per_block = kThreads / G;
+    const int64_t groups_per_block = kThreads / (G * S);
     int64_t blocks = ceil_div(n_items, groups_per_block);
     const int64_t cap = (int64_t)sm_count() * 8 * 4;  // a few waves of resident CTAs; items are interleaved
     if (blocks > cap) blocks = cap;
@@ -178,10 +214,10 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* val, const fl
     do {                                                                                                              \
         if (plan) {                                                                                                   \
             PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h};          \
-            k_spmm<G, VEC, KCH, E, I, MINB, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);    \
+            k_spmm<G, S, VEC, KCH, E, I, MINB, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);    \
         } else {                                                                                                      \
             RowWork w{rowptr, y, ldy};                                                                                \
-            k_spmm<G, VEC, KCH, E, I, MINB, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);     \
+            k_spmm<G, S, VEC, KCH, E, I, MINB, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);     \
         }                                                                                                             \
     } while (0)
     if (exact && idx32) GLASS_SPMM_GO(true, true);
@@ -203,13 +239,23 @@ int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const 
              int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
     const bool vec = (h % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
                      ((uintptr_t)y % 16 == 0) && (!plan || (uintptr_t)plan->scratch % 16 == 0);
-#define GO(G, V, K) return launch<G, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st)
+    const int64_t n_items = plan ? plan->n_items : n_rows;
+    const bool par = latency_regime(n_items);
+#define GO(G, V, K)                                                                                                   \
+    do {                                                                                                              \
+        if (par && G < 32)                                                                                            \
+            return launch<G, 32 / G, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);            \
+        return launch<G, 1, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);                     \
+    } while (0)
     if (vec) {
         const int lanes = h / 4;
         if (lanes <= 2) GO(2, 4, 1);
         if (lanes <= 4) GO(4, 4, 1);
         if (lanes <= 8) GO(8, 4, 1);
-        if (lanes <= 16) return launch<16, 4, 1, 5>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);
+        if (lanes <= 16) {
+            if (par) return launch<16, 2, 4, 1>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);
+            return launch<16, 1, 4, 1, 5>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);
+        }
         if (lanes <= 32) GO(32, 4, 1);
         GO(32, 4, 2);
     } else {

@@ -269,11 +269,23 @@ _ops = torch.ops.glass_b200
 # ---------------------------------------------------------------------------------------------
 # buildAdj -> CSR
 # ---------------------------------------------------------------------------------------------
-SPLIT_ROW_LEN = int(os.environ.get("GLASS_B200_SPLIT_ROW_LEN", "512"))
+SPLIT_ROW_LEN = int(os.environ.get("GLASS_B200_SPLIT_ROW_LEN", "0"))     # 0: chosen per graph
+
+
+def split_row_len(n_rows: int, nnz: int) -> int:
+    """Longest row a single lane group reduces.  Graphs that fill the machine are throughput bound: only
+    hub rows (> 512 entries) are split.  Below about two waves of lanes (same rule as the SpMM dispatcher)
+    the longest row IS the kernel time, so rows are cut at twice the average degree (>= 64)."""
+    if SPLIT_ROW_LEN:
+        return SPLIT_ROW_LEN
+    if n_rows * 32 > 2 * _lib.load().glass_sm_count() * 2048:
+        return 512
+    target = max(64, 2 * nnz // max(n_rows, 1))
+    return min(512, 1 << (target - 1).bit_length())
 
 
 class RowSplitPlan:
-    """Work items for a skewed CSR: rows longer than SPLIT_ROW_LEN entries are cut into chunks that are
+    """Work items for a skewed CSR: rows longer than `max_len` (split_row_len) entries are cut into chunks that are
     reduced by separate lane groups (heavy items first) and summed in chunk order afterwards."""
 
     def __init__(self, rowptr: torch.Tensor, max_len: int):
@@ -308,10 +320,10 @@ class CSRAdj:
         self.rowptr_t, self.col_t, self.val_t = rowptr_t, col_t, val_t
         self.deg = deg
         self.shape = (n, n)
-        self.plan, self.plan_t = plan, plan_t     # RowSplitPlan or None (no row longer than SPLIT_ROW_LEN)
+        self.plan, self.plan_t = plan, plan_t     # RowSplitPlan or None (no row long enough to split)
 
     def make_plans(self, max_len: int = None):
-        max_len = SPLIT_ROW_LEN if max_len is None else max_len
+        max_len = split_row_len(self.n, self.col.numel()) if max_len is None else max_len
         self.plan = self.plan_t = None
         if self.n and self.col.numel():
             p = RowSplitPlan(self.rowptr, max_len)

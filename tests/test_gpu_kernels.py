@@ -124,6 +124,20 @@ def test_spmm_matches_oracle(h):
     assert rel_err(xg.grad.cpu(), ref_gx) < 1e-5
 
 
+@pytest.mark.parametrize("h", [4, 8, 20, 32, 64])
+def test_spmm_both_lane_configurations_match_oracle(h):
+    """n = 3000 (above) runs the neighbour-parallel configuration (32/G slots per row), n = 20000 the
+    one-chain-per-output throughput configuration (spmm.cu latency_regime)."""
+    from glass_b200 import ops
+    n = 20000
+    ei, ew = rand_graph(n, 150000, h)
+    adj = ops.build_csr(ei.to(DEV), ew.to(DEV), n, "gcn")
+    x = torch.randn(n, h, generator=torch.Generator().manual_seed(1))
+    ref = O.build_adj(ei, ew, n, "gcn")
+    assert rel_err(ops.spmm(adj, x.to(DEV)).cpu(), ref @ x) < 1e-5
+    assert rel_err(ops.spmm(adj.t(), x.to(DEV)).cpu(), ref.t() @ x) < 1e-5
+
+
 def test_spmm_is_deterministic_and_sequential_order():
     """Single fp32 FMA chain per output in CSR order: equals a sequential CPU loop bit for bit
     whenever the products are exact (small integers)."""
