@@ -40,6 +40,7 @@ PROTOTYPES = {
                                          _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _sz,
                                          _i32, _vp]),
     "glass_graphnorm_workspace_bytes": (_sz, [_i64, _i32]),
+    "glass_graphnorm_launches": (_i32, [_i64, _i32]),
     "glass_graphnorm_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _f32, _i32, _vp, _f32, _vp, _vp, _i64, _vp, _i64,
                                    _i32, _vp, _sz, _vp]),
     "glass_graphnorm_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _i64, _vp,

@@ -14,7 +14,7 @@
 namespace glass {
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, kThreads = 256;
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, kThreads = 256;  // BK 32 measured 10-40 % slower at K = 17..40
 constexpr int PAD = 4;
 
 struct ASrc {

@@ -11,10 +11,15 @@
 //   dx = rstd*w*u - (rstd*w*S2/N)*yhat - mean_scale*sum_do/N                 (one elementwise pass)
 // Bound: HBM/L2 bandwidth; algorithmic bytes fwd = 4*N*C read twice (second pass is L2-resident) +
 // 4*N*C written (+ N*C mask bytes).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace glass {
 namespace {
+
+namespace cg = cooperative_groups;
 
 constexpr int kThreads = 256;
 constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs (4 per SM measured slower); fixed so the workspace size is device independent
@@ -130,15 +135,18 @@ __device__ __forceinline__ void finalize_fwd_col(const Fin& f, double s, double 
 }
 
 // coef rows: alpha, beta, gamma
-__device__ __forceinline__ void finalize_bwd_col(const Fin& f, double s1, double s2, int64_t n, int c, int col) {
+__device__ __forceinline__ void finalize_bwd_col(const Fin& f, double s1, double s2, int64_t n, int c, int col,
+                                                 bool write_grads = true) {
     const double w = f.weight[col], a = f.mean_scale[col];
     const double rstd = f.stats[ST_RSTD * c + col], mu = f.stats[ST_MU * c + col], am = f.stats[ST_AM * c + col];
     const double N = (double)n;
     const double sum_yhat = rstd * N * (mu - am);
     const double sum_do = rstd * w * (s1 - sum_yhat * s2 / N);
-    f.dweight[col] = (float)s2;
-    f.dbias[col] = (float)s1;
-    f.dmean_scale[col] = (float)(-mu * sum_do);
+    if (write_grads) {
+        f.dweight[col] = (float)s2;
+        f.dbias[col] = (float)s1;
+        f.dmean_scale[col] = (float)(-mu * sum_do);
+    }
     f.coef[0 * c + col] = (float)(rstd * w);
     f.coef[1 * c + col] = (float)(-rstd * w * s2 / N);
     f.coef[2 * c + col] = (float)(-a * sum_do / N);
@@ -322,6 +330,203 @@ k_gn_bwd_apply(const float* __restrict__ dout, int64_t lddo, const float* __rest
     }
 }
 
+
+// ---- small matrices: the whole GraphNorm (forward or backward) as ONE cluster launch -----------------------
+// On tiny matrices the three-kernel pipeline above is pure launch / round-trip latency (5 + 2 + 2 us on a
+// 5,000 x 8 matrix).  Here a cluster of 8 CTAs takes the column sums of its row slices (same fp64
+// accumulation and tree as k_colsums), exchanges the 2c partial sums through distributed shared memory
+// (added in CTA-rank order -> deterministic), every CTA finalises the per-column constants redundantly
+// into its own shared memory, and the element-wise pass re-reads the rows the CTA has just read (L1/L2).
+constexpr int kCl = 8, kClThreads = 512, kClMaxC = 256;
+
+template <int VEC, bool BWD>
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
+k_gn_cluster(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dout, int64_t lddo, const Fin fin,
+             int act, const Drop drop, unsigned long long* rng, float* __restrict__ out, int64_t ldo, int64_t n, int c) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ double sm[2][kClThreads * VEC];
+    __shared__ float s_stats[6 * kClMaxC];
+    __shared__ float s_coef[3 * kClMaxC];
+    __shared__ unsigned long long s_id;
+    const int tid = threadIdx.x;
+    const int CV = (c + VEC - 1) / VEC;
+    const int nrl = kClThreads / CV;                  // row lanes per CTA (host guarantees CV <= kClThreads)
+    const int cvl = tid % CV, rl = tid / CV;
+    const bool active = rl < nrl;
+    const int col = cvl * VEC;
+    const int64_t row0 = (int64_t)rank * nrl + rl, row_stride = (int64_t)kCl * nrl;
+
+    DropCtx dctx{};
+    if (BWD) {
+        for (int i = tid; i < 5 * c; i += kClThreads) s_stats[i] = fin.stats[i];
+        dctx = drop_ctx(drop, fin.stats, c);
+        __syncthreads();
+    } else if (rank == 0 && tid == 0 && drop.rng) {   // id of this call for the dropout generator
+        const unsigned long long id = rng[1];
+        rng[1] = id + 1;
+        s_id = id;
+    }
+
+    // ---- pass 1: column sums of this CTA's rows
+    double s[VEC], q[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) s[k] = q[k] = 0.0;
+    float sc[VEC], am[VEC], rs[VEC], bs[VEC];
+    if (BWD) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const int cc = col + k < c ? col + k : c - 1;
+            sc[k] = s_stats[ST_SCALE * c + cc];
+            am[k] = s_stats[ST_AM * c + cc];
+            rs[k] = s_stats[ST_RSTD * c + cc];
+            bs[k] = s_stats[ST_BIAS * c + cc];
+        }
+    }
+    if (active) {
+#pragma unroll 4
+        for (int64_t r = row0; r < n; r += row_stride) {
+            float xv[VEC], gv[VEC];
+            if (VEC == 4) {
+                const float4 t = ldg_f4(x + r * ldx + col);
+                xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
+                if (BWD) {
+                    const float4 g = ldg_f4(dout + r * lddo + col);
+                    gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+                }
+            } else {
+                xv[0] = x[r * ldx + col];
+                if (BWD) gv[0] = dout[r * lddo + col];
+            }
+            float dm[VEC];
+            if (BWD) drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                if (!BWD) {
+                    s[k] += (double)xv[k];
+                    q[k] += (double)xv[k] * (double)xv[k];
+                } else {
+                    const float o = xv[k] - am[k];
+                    const float pre = fmaf(sc[k], o, bs[k]);
+                    const float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
+                    s[k] += (double)u;
+                    q[k] += (double)u * (double)(o * rs[k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        sm[0][tid * VEC + k] = s[k];
+        sm[1][tid * VEC + k] = q[k];
+    }
+    int span = 1;
+    while (span < nrl) span <<= 1;
+    for (int st = span >> 1; st > 0; st >>= 1) {
+        __syncthreads();
+        if (rl < st && rl + st < nrl) {
+            const int o = (tid + st * CV) * VEC;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                sm[0][tid * VEC + k] += sm[0][o + k];
+                sm[1][tid * VEC + k] += sm[1][o + k];
+            }
+        }
+    }
+    cluster.sync();   // sm[.][col] of every CTA now holds its column sums (row lane 0 owns index col)
+
+    // ---- exchange + finalise (every CTA, redundantly; rank 0 publishes)
+    if (tid < c) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int rk = 0; rk < kCl; ++rk) {
+            const double* remote = cluster.map_shared_rank(&sm[0][0], rk);
+            a += remote[tid];
+            b += remote[kClThreads * VEC + tid];
+        }
+        Fin f = fin;
+        if (!BWD) {
+            f.stats = s_stats;
+            finalize_fwd_col(f, a, b, n, c, tid);
+        } else {
+            f.stats = s_stats;
+            f.coef = s_coef;
+            finalize_bwd_col(f, a, b, n, c, tid, rank == 0);
+        }
+    }
+    if (!BWD && !drop.keep && drop.rng) {
+        const unsigned long long id = *cluster.map_shared_rank(&s_id, 0);
+        const unsigned long long seed = drop.rng[0];
+        dctx.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        dctx.call_lo = (uint32_t)id;
+        dctx.call_hi = c > 1 ? (uint32_t)(id >> 32) : 0u;
+        if (rank == 0 && tid == 0) {
+            fin.stats[ST_RNG * c + 0] = __uint_as_float((uint32_t)id);
+            if (c > 1) fin.stats[ST_RNG * c + 1] = __uint_as_float((uint32_t)(id >> 32));
+        }
+    }
+    cluster.sync();   // remote reads finished; s_stats / s_coef visible to the whole CTA
+    if (!BWD && rank == 0)
+        for (int i = tid; i < 5 * c; i += kClThreads) fin.stats[i] = s_stats[i];
+
+    // ---- pass 2: element-wise, same (row, column) ownership as pass 1
+    if (!active) return;
+    float k0[VEC], k1[VEC], k2[VEC], k3[VEC], k4[VEC], k5[VEC], k6[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        const int cc = col + k < c ? col + k : c - 1;
+        k0[k] = s_stats[ST_SCALE * c + cc];
+        k1[k] = s_stats[ST_AM * c + cc];
+        k2[k] = s_stats[ST_BIAS * c + cc];
+        k3[k] = s_stats[ST_RSTD * c + cc];
+        k4[k] = BWD ? s_coef[0 * c + cc] : 0.f;
+        k5[k] = BWD ? s_coef[1 * c + cc] : 0.f;
+        k6[k] = BWD ? s_coef[2 * c + cc] : 0.f;
+    }
+#pragma unroll 4
+    for (int64_t r = row0; r < n; r += row_stride) {
+        float xv[VEC], gv[VEC], ov[VEC];
+        if (VEC == 4) {
+            const float4 t = ldg_f4(x + r * ldx + col);
+            xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
+            if (BWD) {
+                const float4 g = ldg_f4(dout + r * lddo + col);
+                gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+            }
+        } else {
+            xv[0] = x[r * ldx + col];
+            if (BWD) gv[0] = dout[r * lddo + col];
+        }
+        float dm[VEC];
+        drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float o = xv[k] - k1[k];
+            const float pre = fmaf(k0[k], o, k2[k]);
+            if (!BWD) {
+                ov[k] = act_fwd(pre, act) * dm[k];
+            } else {
+                const float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
+                ov[k] = fmaf(k4[k], u, fmaf(k5[k], o * k3[k], k6[k]));
+            }
+        }
+        if (VEC == 4) *reinterpret_cast<float4*>(out + r * ldo + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        else out[r * ldo + col] = ov[0];
+    }
+}
+
+// Largest matrix (elements) the cluster kernel takes; GLASS_B200_GN_FUSED_MAX overrides (0 disables).
+// Measured fwd+bwd pair, graph replay (scripts/gn_time.py): 10 K elements 19.9 vs 24.1 us (three kernels),
+// 40 K 25.4 vs 26.8, 80 K 29.1 vs 25.2, 160 K 38.7 vs 25.7 -- eight SMs run out of issue slots (Philox, ELU,
+// fp64 sums) long before the data is large, so the cut-over is low.
+inline bool use_cluster(int64_t n, int c, int vec) {
+    static const int64_t max_elems = [] {
+        const char* e = getenv("GLASS_B200_GN_FUSED_MAX");
+        return e ? (int64_t)atoll(e) : (int64_t)48 * 1024;
+    }();
+    return c <= kClMaxC && (c + vec - 1) / vec <= kClThreads && n * (int64_t)c <= max_elems;
+}
+
 inline Drop make_drop(const uint8_t* keep, const unsigned long long* rng, float p) {
     Drop d{};
     d.pscale = 1.f;
@@ -365,6 +570,11 @@ extern "C" size_t glass_graphnorm_workspace_bytes(int64_t n, int c) {
     return align_up((size_t)kMaxPartialCtas * 2 * (size_t)c * sizeof(double), 256) + align_up(3 * (size_t)c * sizeof(float), 256);
 }
 
+extern "C" int glass_graphnorm_launches(int64_t n, int c) {
+    if (n <= 0 || c <= 0) return 0;
+    return use_cluster(n, c, c % 4 == 0 ? 4 : 1) ? 1 : 3;
+}
+
 extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                                    const float* mean_scale, float eps, int act, const uint8_t* keep, float drop_p,
                                    unsigned long long* rng, float* out, int64_t ldo, float* stats, int64_t n, int c,
@@ -381,9 +591,16 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     Fin fin{};
     fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats;
+    GLASS_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "graphnorm_fwd: dropout p must be in [0, 1)");
+    if (use_cluster(n, c, vec ? 4 : 1)) {
+        const Drop d = make_drop(keep, rng, drop_p);
+        if (vec) k_gn_cluster<4, false><<<kCl, kClThreads, 0, st>>>(x, ldx, nullptr, 0, fin, act, d, rng, out, ldo, n, c);
+        else k_gn_cluster<1, false><<<kCl, kClThreads, 0, st>>>(x, ldx, nullptr, 0, fin, act, d, rng, out, ldo, n, c);
+        GLASS_LAUNCH_CHECK();
+        return GLASS_OK;
+    }
     if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
     else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
-    GLASS_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "graphnorm_fwd: dropout p must be in [0, 1)");
     const Drop drop = make_drop(keep, rng, drop_p);
     k_gn_finalize<false><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, drop.rng ? rng : nullptr);
     const int64_t work = n * (vec ? c / 4 : c);
@@ -417,6 +634,12 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
     fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
     fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale;
     const Drop drop = make_drop(keep, rng, drop_p);
+    if (use_cluster(n, c, vec ? 4 : 1)) {
+        if (vec) k_gn_cluster<4, true><<<kCl, kClThreads, 0, st>>>(x, ldx, dout, lddo, fin, act, drop, nullptr, dx, lddx, n, c);
+        else k_gn_cluster<1, true><<<kCl, kClThreads, 0, st>>>(x, ldx, dout, lddo, fin, act, drop, nullptr, dx, lddx, n, c);
+        GLASS_LAUNCH_CHECK();
+        return GLASS_OK;
+    }
     if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
     else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
     k_gn_finalize<true><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, nullptr);

@@ -95,24 +95,34 @@ __global__ void k_embed_fwd(const float* __restrict__ table, const int64_t* __re
     }
 }
 
-// Gradient of the lookup: each CTA walks a contiguous chunk of rows, keeps a running sum while the
-// id does not change and flushes with one atomicAdd per (run, column).  Constant ids (--use_one)
-// cost one atomic per CTA and column; arange ids (--use_nodeid) one uncontended atomic per element.
+// Gradient of the lookup: each CTA walks RPC consecutive rows, keeps a running sum while the id does not
+// change and flushes with one atomicAdd per (run, column).  Constant ids (--use_one) cost one atomic per
+// CTA and column; arange ids (--use_nodeid) one uncontended atomic per element.  All RPC (id, value) pairs
+// are loaded before the run-length pass, so the kernel is one load round, not RPC dependent ones.
+constexpr int kEmbedRowsPerCta = 16;
 __global__ void k_embed_bwd(const float* __restrict__ dout, int64_t lddo, const int64_t* __restrict__ ids,
-                            float* __restrict__ dtable, int64_t n, int64_t rows, int h, int rows_per_cta) {
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-    int64_t r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
+                            float* __restrict__ dtable, int64_t n, int64_t rows, int h) {
+    constexpr int RPC = kEmbedRowsPerCta;
+    const int64_t r0 = (int64_t)blockIdx.x * RPC;
     for (int c = threadIdx.x; c < h; c += blockDim.x) {
+        int64_t id[RPC];
+        float v[RPC];
+#pragma unroll
+        for (int i = 0; i < RPC; ++i) {
+            const bool ok = r0 + i < n;
+            id[i] = ok ? ids[r0 + i] : -1;
+            v[i] = ok ? dout[(r0 + i) * lddo + c] : 0.f;
+        }
         float acc = 0.f;
         int64_t cur = -1;
-        for (int64_t r = r0; r < r1; ++r) {
-            int64_t id = ids[r];
-            if (id != cur) {
+#pragma unroll
+        for (int i = 0; i < RPC; ++i) {
+            if (id[i] != cur) {
                 if (cur >= 0 && cur < rows) atomicAdd(dtable + cur * h + c, acc);
-                cur = id;
+                cur = id[i];
                 acc = 0.f;
             }
-            acc += dout[r * lddo + c];
+            acc += v[i];
         }
         if (cur >= 0 && cur < rows) atomicAdd(dtable + cur * h + c, acc);
     }
@@ -180,10 +190,9 @@ extern "C" int glass_embedding_bwd(const float* dout, int64_t lddo, const int64_
                                    int64_t rows, int h, void* stream) {
     GLASS_CHECK_ARG(dout && ids && dtable && n >= 0 && rows > 0 && h > 0 && lddo >= h, "embedding_bwd: bad arguments");
     if (n == 0) return GLASS_OK;
-    const int rows_per_cta = 32;
     int threads = h < 32 ? 32 : (h > 256 ? 256 : (h + 31) / 32 * 32);
-    k_embed_bwd<<<(unsigned)ceil_div(n, rows_per_cta), threads, 0, as_stream(stream)>>>(dout, lddo, ids, dtable, n, rows,
-                                                                                      h, rows_per_cta);
+    k_embed_bwd<<<(unsigned)ceil_div(n, kEmbedRowsPerCta), threads, 0, as_stream(stream)>>>(dout, lddo, ids, dtable, n,
+                                                                                          rows, h);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

@@ -156,7 +156,7 @@ def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, drop_p, rng, out, stat
     check(lib.glass_graphnorm_fwd(_p(x), x.stride(0), _p(weight), _p(bias), _p(mean_scale), eps, act, _p(keep),
                                   drop_p, _p(rng), _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
                                   workspace.numel(), _stream()), "graphnorm_fwd")
-    _count(3)
+    _count(lib.glass_graphnorm_launches(n, c))
 
 
 _define("graphnorm_fwd_(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, int act, Tensor? keep, "
@@ -170,7 +170,7 @@ def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, dx, dwe
                                   _p(stats), act, _p(keep), drop_p, _p(rng), _p(dx), dx.stride(0), _p(dweight),
                                   _p(dbias), _p(dmean_scale), n, c, _p(workspace), workspace.numel(), _stream()),
           "graphnorm_bwd")
-    _count(3)
+    _count(lib.glass_graphnorm_launches(n, c))
 
 
 _define("graphnorm_bwd_(Tensor dout, Tensor x, Tensor weight, Tensor mean_scale, Tensor stats, int act, Tensor? keep, "

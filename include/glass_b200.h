@@ -132,8 +132,12 @@ int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts
  * them from the id saved in `stats`; with both NULL there is no dropout.
  * Column sums are accumulated in fp64 per block and reduced in block order (deterministic).
  * workspace: glass_graphnorm_workspace_bytes(n, c).
+ * Matrices of at most 48 K elements (c <= 256) run as ONE launch on a thread-block cluster (partials
+ * exchanged through distributed shared memory); larger ones as three (sums, finalise, element-wise).
+ * glass_graphnorm_launches(n, c) tells which (1 or 3; pure host arithmetic, for launch accounting).
  * ------------------------------------------------------------------------------------------ */
 size_t glass_graphnorm_workspace_bytes(int64_t n, int c);
+int glass_graphnorm_launches(int64_t n, int c);
 int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                         const float* mean_scale, float eps, int act, const uint8_t* keep, float drop_p,
                         unsigned long long* rng, float* out, int64_t ldo, float* stats, int64_t n, int c,

@@ -236,8 +236,13 @@ def test_pair_linear_mix_fwd_bwd(n, k1, k2, h, act, z, path):
 
 # ------------------------------------------------------------------------------------------ GraphNorm
 @pytest.mark.parametrize("n,c,act,p", [(1000, 64, 0, 0.0), (999, 64, 2, 0.5), (300, 17, 0, 0.3), (257, 20, 1, 0.05),
-                                       (5000, 128, 2, 0.0), (64, 8, 0, 0.0), (2000, 256, 2, 0.2)])
+                                       (5000, 128, 2, 0.0), (64, 8, 0, 0.0), (2000, 256, 2, 0.2),
+                                       (20000, 17, 2, 0.3), (30000, 8, 1, 0.1), (12000, 20, 0, 0.0),
+                                       (600, 256, 2, 0.2), (5000, 8, 2, 0.0), (7, 4, 0, 0.0),
+                                       (180, 256, 2, 0.2), (700, 64, 2, 0.5)])
 def test_graph_norm_fwd_bwd(n, c, act, p):
+    """Matrices up to 48 K elements take the one-launch cluster kernel, larger ones the three-kernel path
+    (glass_graphnorm_launches); both are covered for vector (c % 4 == 0) and scalar column layouts."""
     from glass_b200 import ops
     g = torch.Generator().manual_seed(n + c)
     x = torch.randn(n, c, generator=g) * 3 + torch.randn(1, c, generator=g) * 5   # non-zero column means
