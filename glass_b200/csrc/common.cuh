@@ -58,6 +58,13 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
     return 1.f;
 }
 
+// the same derivative from the PRE-activation value: exp(x) has no cancellation near 0, so no expm1 blend
+__device__ __forceinline__ float act_grad_from_pre(float v, int act) {
+    if (act == GLASS_ACT_RELU) return v > 0.f ? 1.f : 0.f;
+    if (act == GLASS_ACT_ELU) return v > 0.f ? 1.f : __expf(v);
+    return 1.f;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -22,6 +22,7 @@ namespace {
 namespace cg = cooperative_groups;
 
 constexpr int kThreads = 256;
+constexpr int kSumThreads = 256;      // k_colsums; 512 threads per CTA measured slower (em_user bwd 14.6 -> 19.2 us per launch)
 constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs (4 per SM measured slower); fixed so the workspace size is device independent
 
 // stats rows
@@ -153,18 +154,18 @@ __device__ __forceinline__ void finalize_bwd_col(const Fin& f, double s1, double
 }
 
 template <int VEC, bool BWD>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kSumThreads)
 k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dout, int64_t lddo,
           const float* __restrict__ stats, const float* __restrict__ bias, int act, const Drop drop, int64_t n, int c,
           double* __restrict__ partial) {
     const DropCtx dctx = BWD ? drop_ctx(drop, stats, c) : DropCtx{};
     // thread -> (column vector cvl, row lane rl).  CVB column vectors are processed per pass.
     const int CV = (c + VEC - 1) / VEC;
-    const int CVB = CV < kThreads ? CV : kThreads;
-    const int nrl = kThreads / CVB;
+    const int CVB = CV < kSumThreads ? CV : kSumThreads;
+    const int nrl = kSumThreads / CVB;
     const int cvl = threadIdx.x % CVB, rl = threadIdx.x / CVB;
     const bool active = rl < nrl;
-    __shared__ double sm[2][kThreads * VEC];
+    __shared__ double sm[2][kSumThreads * VEC];
     for (int cv0 = 0; cv0 < CV; cv0 += CVB) {
         const int cv = cv0 + cvl;
         double s[VEC], q[VEC];
@@ -207,7 +208,7 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
                     } else {
                         float o = xv[k] - am[k];
                         float pre = fmaf(sc[k], o, bs[k]);
-                        float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
+                        float u = gv[k] * act_grad_from_pre(pre, act) * dm[k];
                         s[k] += (double)u;
                         q[k] += (double)u * (double)(o * rs[k]);
                     }
@@ -265,71 +266,112 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const double* partial, int 
     else finalize_fwd_col(fin, a, b, n, c, col);
 }
 
+constexpr int kApplyCtasPerSm = 4, kBwdApplyCtasPerSm = 3;   // resident CTAs (registers); grids are one wave
+
+// Element-wise passes.  A thread owns one column vector (VEC consecutive columns) and walks rows, so the
+// per-column constants live in registers and there is no index division in the loop (the first version
+// mapped a flat element index with a 64-bit div/mod and re-read the constants per element: 300 instructions
+// per float4, 70 % issue-slot utilisation -- instruction bound, not memory bound).
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kApplyCtasPerSm)
 k_gn_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ stats, const float* __restrict__ bias,
            int act, const Drop drop, float* __restrict__ out, int64_t ldo, int64_t n, int c) {
     const DropCtx dctx = drop_ctx(drop, stats, c);
     const int CV = (c + VEC - 1) / VEC;
-    const int64_t total = n * CV, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int64_t r = e / CV;
-        const int col = (int)(e % CV) * VEC;
-        float xv[VEC], ov[VEC];
-        if (VEC == 4) {
-            float4 t = ldg_f4(x + r * ldx + col);
-            xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
-        } else {
-            xv[0] = x[r * ldx + col];
-        }
-        float dm[VEC];
-        drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+    const int CVB = CV < kThreads ? CV : kThreads;
+    const int nrl = kThreads / CVB;
+    const int cvl = threadIdx.x % CVB, rl = threadIdx.x / CVB;
+    if (rl >= nrl) return;
+    const int64_t row0 = (int64_t)blockIdx.x * nrl + rl, row_stride = (int64_t)gridDim.x * nrl;
+    for (int cv = cvl; cv < CV; cv += CVB) {
+        const int col = cv * VEC;
+        float sc[VEC], am[VEC], bs[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            float pre = fmaf(stats[ST_SCALE * c + col + k], xv[k] - stats[ST_AM * c + col + k], bias[col + k]);
-            ov[k] = act_fwd(pre, act) * dm[k];
+            const int cc = col + k < c ? col + k : c - 1;
+            sc[k] = stats[ST_SCALE * c + cc];
+            am[k] = stats[ST_AM * c + cc];
+            bs[k] = bias[cc];
         }
-        if (VEC == 4) *reinterpret_cast<float4*>(out + r * ldo + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        else out[r * ldo + col] = ov[0];
+#pragma unroll 4
+        for (int64_t r = row0; r < n; r += row_stride) {
+            float xv[VEC], ov[VEC];
+            if (VEC == 4) {
+                const float4 t = ldg_f4(x + r * ldx + col);
+                xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
+            } else {
+                xv[0] = x[r * ldx + col];
+            }
+            float dm[VEC];
+            drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) ov[k] = act_fwd(fmaf(sc[k], xv[k] - am[k], bs[k]), act) * dm[k];
+            if (VEC == 4) *reinterpret_cast<float4*>(out + r * ldo + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            else out[r * ldo + col] = ov[0];
+        }
     }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kBwdApplyCtasPerSm)
 k_gn_bwd_apply(const float* __restrict__ dout, int64_t lddo, const float* __restrict__ x, int64_t ldx,
                const float* __restrict__ stats, const float* __restrict__ bias, const float* __restrict__ coef, int act,
                const Drop drop, float* __restrict__ dx, int64_t lddx, int64_t n, int c) {
     const DropCtx dctx = drop_ctx(drop, stats, c);
     const int CV = (c + VEC - 1) / VEC;
-    const int64_t total = n * CV, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int64_t r = e / CV;
-        const int col = (int)(e % CV) * VEC;
-        float xv[VEC], gv[VEC], ov[VEC];
-        if (VEC == 4) {
-            float4 t = ldg_f4(x + r * ldx + col), g = ldg_f4(dout + r * lddo + col);
-            xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
-            gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
-        } else {
-            xv[0] = x[r * ldx + col];
-            gv[0] = dout[r * lddo + col];
-        }
-        float dm[VEC];
-        drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+    const int CVB = CV < kThreads ? CV : kThreads;
+    const int nrl = kThreads / CVB;
+    const int cvl = threadIdx.x % CVB, rl = threadIdx.x / CVB;
+    if (rl >= nrl) return;
+    const int64_t row0 = (int64_t)blockIdx.x * nrl + rl, row_stride = (int64_t)gridDim.x * nrl;
+    for (int cv = cvl; cv < CV; cv += CVB) {
+        const int col = cv * VEC;
+        float sc[VEC], am[VEC], bs[VEC], rs[VEC], c0[VEC], c1[VEC], c2[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const int cc = col + k;
-            float o = xv[k] - stats[ST_AM * c + cc];
-            float pre = fmaf(stats[ST_SCALE * c + cc], o, bias[cc]);
-            float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
-            float yhat = o * stats[ST_RSTD * c + cc];
-            ov[k] = fmaf(coef[0 * c + cc], u, fmaf(coef[1 * c + cc], yhat, coef[2 * c + cc]));
+            const int cc = col + k < c ? col + k : c - 1;
+            sc[k] = stats[ST_SCALE * c + cc];
+            am[k] = stats[ST_AM * c + cc];
+            rs[k] = stats[ST_RSTD * c + cc];
+            bs[k] = bias[cc];
+            c0[k] = coef[0 * c + cc];
+            c1[k] = coef[1 * c + cc];
+            c2[k] = coef[2 * c + cc];
         }
-        if (VEC == 4) *reinterpret_cast<float4*>(dx + r * lddx + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        else dx[r * lddx + col] = ov[0];
+#pragma unroll 4
+        for (int64_t r = row0; r < n; r += row_stride) {
+            float xv[VEC], gv[VEC], ov[VEC];
+            if (VEC == 4) {
+                const float4 t = ldg_f4(x + r * ldx + col), g = ldg_f4(dout + r * lddo + col);
+                xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
+                gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+            } else {
+                xv[0] = x[r * ldx + col];
+                gv[0] = dout[r * lddo + col];
+            }
+            float dm[VEC];
+            drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float o = xv[k] - am[k];
+                const float u = gv[k] * act_grad_from_pre(fmaf(sc[k], o, bs[k]), act) * dm[k];
+                ov[k] = fmaf(c0[k], u, fmaf(c1[k], o * rs[k], c2[k]));
+            }
+            if (VEC == 4) *reinterpret_cast<float4*>(dx + r * lddx + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            else dx[r * lddx + col] = ov[0];
+        }
     }
 }
 
+// grid of the element-wise kernels: at least 4 rows per thread, at most one wave of resident CTAs
+inline unsigned apply_ctas(int64_t n, int c, int vec, int ctas_per_sm) {
+    const int cv = (c + vec - 1) / vec;
+    const int cvb = cv < kThreads ? cv : kThreads;
+    const int nrl = kThreads / cvb;
+    int64_t want = ceil_div(n, (int64_t)nrl * 4);
+    if (want < 1) want = 1;
+    return (unsigned)std::min<int64_t>(want, (int64_t)sm_count() * ctas_per_sm);
+}
 
 // ---- small matrices: the whole GraphNorm (forward or backward) as ONE cluster launch -----------------------
 // On tiny matrices the three-kernel pipeline above is pure launch / round-trip latency (5 + 2 + 2 us on a
@@ -408,7 +450,7 @@ k_gn_cluster(const float* __restrict__ x, int64_t ldx, const float* __restrict__
                 } else {
                     const float o = xv[k] - am[k];
                     const float pre = fmaf(sc[k], o, bs[k]);
-                    const float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
+                    const float u = gv[k] * act_grad_from_pre(pre, act) * dm[k];
                     s[k] += (double)u;
                     q[k] += (double)u * (double)(o * rs[k]);
                 }
@@ -506,7 +548,7 @@ k_gn_cluster(const float* __restrict__ x, int64_t ldx, const float* __restrict__
             if (!BWD) {
                 ov[k] = act_fwd(pre, act) * dm[k];
             } else {
-                const float u = gv[k] * act_grad_from_out(act_fwd(pre, act), act) * dm[k];
+                const float u = gv[k] * act_grad_from_pre(pre, act) * dm[k];
                 ov[k] = fmaf(k4[k], u, fmaf(k5[k], o * k3[k], k6[k]));
             }
         }
@@ -544,8 +586,8 @@ inline Drop make_drop(const uint8_t* keep, const unsigned long long* rng, float 
 
 inline int partial_ctas(int64_t n, int c, int vec) {
     int cv = (c + vec - 1) / vec;
-    int cvb = cv < kThreads ? cv : kThreads;
-    int nrl = kThreads / cvb;
+    int cvb = cv < kSumThreads ? cv : kSumThreads;
+    int nrl = kSumThreads / cvb;
     int64_t want = ceil_div(n, (int64_t)nrl * 4);  // >= 4 rows per thread
     if (want < 1) want = 1;
     return (int)(want < kMaxPartialCtas ? want : kMaxPartialCtas);
@@ -599,12 +641,11 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
     }
-    if (vec) k_colsums<4, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
-    else k_colsums<1, false><<<nblk, kThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
+    if (vec) k_colsums<4, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
+    else k_colsums<1, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
     const Drop drop = make_drop(keep, rng, drop_p);
     k_gn_finalize<false><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, drop.rng ? rng : nullptr);
-    const int64_t work = n * (vec ? c / 4 : c);
-    unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
+    const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kApplyCtasPerSm);
     if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
     else k_gn_apply<1><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
     GLASS_LAUNCH_CHECK();
@@ -640,11 +681,10 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
     }
-    if (vec) k_colsums<4, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
-    else k_colsums<1, true><<<nblk, kThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
+    if (vec) k_colsums<4, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
+    else k_colsums<1, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
     k_gn_finalize<true><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, nullptr);
-    const int64_t work = n * (vec ? c / 4 : c);
-    unsigned grid = (unsigned)std::min<int64_t>(ceil_div(work, kThreads), (int64_t)sm_count() * 8);
+    const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kBwdApplyCtasPerSm);
     if (vec) k_gn_bwd_apply<4><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
     else k_gn_bwd_apply<1><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
     GLASS_LAUNCH_CHECK();

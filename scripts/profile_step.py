@@ -24,9 +24,13 @@ for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
         import re
         m = re.search(r"(k_[A-Za-z0-9_]+(?:<[^>]*>)?)", e.name)
-        name = m.group(1)[:40] if m else e.name[:40]
+        if m:
+            name = m.group(1)[:40]
+        else:   # torch kernels: keep the functor, it tells which op launched it
+            f = re.search(r"(\w+Functor\w*|\w+_kernel_cuda\w*|\w+Op<|\w+Ops<|\w+Impl\b)", e.name)
+            name = (e.name[:24] + ".." + f.group(1)[:28]) if f else e.name[:56]
         a_ = agg.setdefault(name, [0, 0.0]); a_[0] += 1; a_[1] += e.device_time
 tot = sum(v[1] for v in agg.values())
 print(f"20 graph replays: kernel time {tot/20:.1f} us/step")
-for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:44]:
     print(f"{t/20:8.1f} us/step  x{c/20:4.1f}  {k}")
