@@ -319,6 +319,11 @@ def run_product(args):
             line["gpu_eager_baseline"] = {"value": v, "unit": "subgraphs/s", "ms_per_step": per * 1e3,
                                           "what": "oracle port of impl/models.py run eagerly on this GPU "
                                                   "(torch.sparse COO @ dense -> cuSPARSE, ATen element-wise, torch Adam)"}
+        if world == 1 and args.workload == "em_user_shaped" and not args.no_other_configs:
+            del fwd, step
+            line["other_configs"] = {name: quick_config(name, dev, args.steps, args.warmup,
+                                                        0 if args.no_cpu_baseline else args.cpu_steps)
+                                     for name in OTHER_CONFIGS}
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels are still alive; tearing the communicator down under them
@@ -330,6 +335,45 @@ def run_product(args):
         os._exit(0)
 
 
+OTHER_CONFIGS = ("density", "cut_ratio", "component", "ppi_bp_shaped")   # BASELINE.json configs[0..2]
+
+
+def quick_config(name, dev, steps, warmup, cpu_steps):
+    """Device-timed graph-replayed train steps of another BASELINE.json config (batches resident in HBM) and
+    the CPU port beside it; reported under `other_configs`, not part of the headline value."""
+    from glass_b200 import ops, run
+    from glass_b200.graphed import GraphedTrainStep
+    wl = make_workload(name)
+    p, g = wl["params"], wl["g"]
+    torch.manual_seed(0)
+    model = run.build_model(p["hidden_dim"], p["conv_layer"], p["dropout"], 1, p["pool"], p["z_ratio"], p["aggr"],
+                            wl["max_deg"], wl["out_dim"], pretrained=wl["table"], device=dev)
+    x, ei, ew = g.x.to(dev), g.edge_index.to(dev), g.edge_attr.to(dev)
+    batches = [(pos.to(dev), y.to(dev)) for pos, y in batches_for(wl, warmup + steps, 0, 1)]
+    ops.reset_launch_count()
+    step = GraphedTrainStep(model, wl["loss_fn"], x, ei, ew, batches[0][0], batches[0][1], p["lr"], warmup=3)
+    ops.reset_launch_count()
+    step.capture()
+    launches = ops.launch_count()
+    for pos, y in batches[:warmup]:
+        step(pos, y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for pos, y in batches[warmup:]:
+        step(pos, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": p["batch_size"] / (ms * 1e-3), "unit": "subgraphs/s", "ms_per_step": ms,
+           "gpu_launches_per_step": launches, "nodes": int(g.x.shape[0]), "nnz": int(model.conv.convs[0].adj.nnz),
+           "hidden_dim": p["hidden_dim"], "conv_layer": p["conv_layer"], "batch_size": p["batch_size"]}
+    if cpu_steps:
+        v, per = cpu_port_steps(wl, cpu_steps, 1)
+        out["cpu_port"] = {"value": v, "ms_per_step": per * 1e3, "cores": torch.get_num_threads()}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,6 +383,8 @@ def main():
     ap.add_argument("--workload", default="em_user_shaped")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short runs of the other BASELINE.json configs (`other_configs` key)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--gpu-eager-baseline", action="store_true",
                     help="also time the reference's eager torch.sparse op sequence on this GPU (extra key)")
