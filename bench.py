@@ -212,7 +212,8 @@ def spmm_roofline(adj, h: int, reps: int = 20):
     return {"bound": "hbm", "kernel": "k_spmm (glass_spmm_csr)", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": algo, "us_per_launch": avg * 1e3,
             "us_min": ms[0] * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-            "gather_bytes_l2": 4 * h * adj.nnz}
+            "gather_bytes_l2": 4 * h * adj.nnz, "gather_gbs_l2": 4 * h * adj.nnz / (avg * 1e-3) / 1e9,
+            "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0}
 
 
 def run_product(args):

@@ -49,6 +49,35 @@ def test_label_batch_dp_gloo_world2():
     assert g0 == g1                                     # averaged gradients identical on both ranks
 
 
+def _eval_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from glass_b200 import train
+    from glass_b200.dist import sharded_test
+    torch.manual_seed(3)
+    model = torch.nn.Linear(4, 3)
+    g = torch.Generator().manual_seed(1)
+    sizes = [3, 1, 4, 2, 5]                                # odd batch count, ragged last batches
+    batches = [(torch.randn(n, 4, generator=g), torch.randint(0, 3, (n,), generator=g)) for n in sizes]
+    metric = lambda pred, y: float((pred.argmax(-1) == y).mean())
+    loss_fn = torch.nn.CrossEntropyLoss()
+    ref_score, ref_loss = train.test(model, batches, metric, loss_fn)
+    score, loss = sharded_test(model, batches, metric, loss_fn)
+    out[rank] = (ref_score, float(ref_loss), score, float(loss))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_eval_matches_single_device_eval_gloo_world2():
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_eval_worker, args=(world, 29533, out), nprocs=world, join=True)
+    for r in range(world):
+        ref_score, ref_loss, score, loss = out[r]
+        assert score == ref_score and abs(loss - ref_loss) < 1e-6
+
+
 def test_shard_batches_drops_remainder():
     from glass_b200.dist import shard_batches
     assert shard_batches(7, 0, 2) == [0, 2, 4] and shard_batches(7, 1, 2) == [1, 3, 5]
