@@ -6,7 +6,7 @@ GLASSTest.py (flags :14-30, seeding :34-47, split :77-126, buildModel :129-175, 
 
 Differences: runs on a CUDA device only (no --device -1), `--use_nodeid` on a *_shaped synthetic dataset uses
 a seeded stand-in embedding table (the reference's Emb/<dataset>_64.pt files are not shipped), and
-`--graph` replays each training step as one CUDA graph.
+`--graph` replays each training step and each evaluation batch as one CUDA graph.
 """
 import argparse
 import random
@@ -17,7 +17,7 @@ import torch
 from torch.optim import Adam, lr_scheduler
 
 from glass_b200 import SubGDataset, config, datasets, ops, run, train, utils
-from glass_b200.graphed import GraphedTrainStep, train_epoch
+from glass_b200.graphed import GraphedForward, GraphedTrainStep, test_epoch, train_epoch
 
 
 def parse_args():
@@ -106,6 +106,14 @@ class Experiment:
                 step = GraphedTrainStep(gnn, self.loss_fn, self.trn.x, self.trn.edge_index, self.trn.edge_attr,
                                         self.trn.pos[:batch_size], self.trn.y[:batch_size], lr).capture()
                 step.reset_to(init)
+                example = self.val.pos.new_full((batch_size, self.val.pos.shape[1]), -1)
+                k = min(batch_size, self.val.pos.shape[0])
+                example[:k] = self.val.pos[:k]
+                fwd = GraphedForward(gnn, self.trn.x, self.trn.edge_index, self.trn.edge_attr, example)
+            if step is None:
+                evaluate = lambda loader: train.test(gnn, loader, self.score_fn, loss_fn=self.loss_fn)
+            else:
+                evaluate = lambda loader: test_epoch(fwd, loader, self.score_fn, self.loss_fn)
             val_score = tst_score = 0
             early_stop = 0
             trn_time = []
@@ -114,27 +122,27 @@ class Experiment:
                 if step is None:
                     loss = train.train(optimizer, gnn, trn_loader, self.loss_fn)
                 else:
-                    loss = train_epoch(step, ((b[3], b[5]) for b in trn_loader))
+                    loss = train_epoch(step, SubGDataset.epoch_batches(trn_loader), sync_each_step=False)
                 torch.cuda.synchronize()
                 trn_time.append(time.time() - t1)
                 scd.step(loss)
                 if step is not None:
                     step.set_lr(optimizer.param_groups[0]["lr"])
                 if i >= 100 / num_div:
-                    score, _ = train.test(gnn, val_loader, self.score_fn, loss_fn=self.loss_fn)
+                    score, _ = evaluate(val_loader)
                     if score > val_score:
                         early_stop = 0
                         val_score = score
-                        tst_score, _ = train.test(gnn, tst_loader, self.score_fn, loss_fn=self.loss_fn)
+                        tst_score, _ = evaluate(tst_loader)
                         print(f"iter {i} loss {loss:.4f} val {val_score:.4f} tst {tst_score:.4f}", flush=True)
                     elif score >= val_score - 1e-5:
-                        score, _ = train.test(gnn, tst_loader, self.score_fn, loss_fn=self.loss_fn)
+                        score, _ = evaluate(tst_loader)
                         tst_score = max(score, tst_score)
                         print(f"iter {i} loss {loss:.4f} val {val_score:.4f} tst {score:.4f}", flush=True)
                     else:
                         early_stop += 1
                         if i % 10 == 0:
-                            s = train.test(gnn, tst_loader, self.score_fn, loss_fn=self.loss_fn)[0]
+                            s = evaluate(tst_loader)[0]
                             print(f"iter {i} loss {loss:.4f} val {score:.4f} tst {s:.4f}", flush=True)
                 if val_score >= 1 - 1e-5:
                     early_stop += 1

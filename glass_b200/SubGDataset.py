@@ -70,3 +70,33 @@ class ZGDataloader(GDataloader):
         perm = next(self.iter)
         tpos = self.get_pos()[perm]
         return self.get_x(), self.get_ei(), self.get_ea(), tpos, self.z_fn(self.get_x(), tpos), self.get_y()[perm]
+
+
+def index_batches(loader: GDataloader):
+    """The index batches `iter(loader)` would produce, as CPU int64 tensors, drawing from torch's global RNG
+    in the same order as torch.utils.data.DataLoader does (the iterator's base seed first, then the
+    RandomSampler's own seed on its first draw), so a seeded run sees the same subgraph order whichever
+    way the epoch is iterated.  tests/test_host_logic.py pins this against DataLoader itself."""
+    if loader.generator is None:
+        torch.empty((), dtype=torch.int64).random_()          # _BaseDataLoaderIter.__init__: self._base_seed
+    else:
+        torch.empty((), dtype=torch.int64).random_(generator=loader.generator)
+    for idx in loader.batch_sampler:
+        yield torch.as_tensor(idx, dtype=torch.int64)
+
+
+def epoch_batches(loader: GDataloader):
+    """(subG_node, y) of every batch of one epoch in the loader's order, for the captured train / eval
+    steps: one gather of the whole epoch instead of one per batch, no per-batch z_fn (the captured step
+    computes the labels itself), no per-batch collation of device scalars."""
+    batches = list(index_batches(loader))
+    if not batches:
+        return
+    pos, y = loader.get_pos(), loader.get_y()
+    order = torch.cat(batches).to(pos.device, non_blocking=True)
+    pos_e, y_e = pos[order], y[order]
+    off = 0
+    for b in batches:
+        n = b.numel()
+        yield pos_e[off:off + n], y_e[off:off + n]
+        off += n

@@ -159,3 +159,23 @@ def train_epoch(step: GraphedTrainStep, batches, sync_each_step: bool = True) ->
     if sync_each_step:
         return sum(losses) / len(losses)
     return float(torch.stack(losses).double().sum().item()) / len(losses)
+
+
+@torch.no_grad()
+def test_epoch(fwd: GraphedForward, loader, metrics, loss_fn):
+    """impl/train.py:20-34 with the captured forward.  A ragged last batch (drop_last=False loaders) is
+    padded with empty subgraphs (rows of -1): they add no labels, pool to zero, and their logits are dropped,
+    so the result equals train.test on the same loader."""
+    from .SubGDataset import epoch_batches
+    cap = fwd.pos.shape[0]
+    preds, ys = [], []
+    for pos, y in epoch_batches(loader):
+        n = pos.shape[0]
+        if n > cap:
+            raise RuntimeError(f"batch of {n} subgraphs exceeds the captured batch size {cap}")
+        if n < cap:
+            pos = torch.cat((pos, pos.new_full((cap - n, pos.shape[1]), -1)), dim=0)
+        preds.append(fwd(pos)[:n].clone())
+        ys.append(y)
+    pred, y = torch.cat(preds, dim=0), torch.cat(ys, dim=0)
+    return metrics(pred.cpu().numpy(), y.cpu().numpy()), loss_fn(pred, y)

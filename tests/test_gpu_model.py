@@ -308,6 +308,32 @@ def test_cuda_graph_replays_draw_fresh_dropout_masks():
     assert torch.allclose(fwd(pos), ref, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["ppibp_like", "emuser_like"])
+def test_graphed_eval_epoch_matches_train_test_on_ragged_loader(name):
+    """graphed.test_epoch (captured forward, last batch padded with empty subgraphs, one gather per epoch)
+    returns what train.test returns on the same loader in the same seeded order."""
+    from glass_b200 import SubGDataset, train, utils
+    from glass_b200.graphed import GraphedForward, test_epoch
+    c = load_model_case(name)
+    x, ei, ew, pos, _ = _dev(c)
+    y = c["y"].to(DEV)
+    reps = 7 // pos.shape[0] + 1                           # 7+ subgraphs, batch size 3 -> ragged last batch
+    pos7, y7 = pos.repeat(reps, 1)[:7].clone(), y.repeat(*([reps] + [1] * (y.dim() - 1)))[:7].clone()
+    pos7[1:] = pos7[1:].roll(1, dims=1)
+    ds = SubGDataset.GDataset(x, ei, ew, pos7, y7)
+    loader = SubGDataset.ZGDataloader(ds, 3, z_fn=utils.MaxZOZ, shuffle=True, drop_last=False)
+    m = _product_from_case(c).eval()
+    loss_fn = O.loss_fn_for(c["cfg"].out_dim == 1)
+    metric = lambda pred, t: float(np.abs(pred).sum())
+    torch.manual_seed(5)
+    ref_score, ref_loss = train.test(m, loader, metric, loss_fn)
+    fwd = GraphedForward(m, x, ei, ew, pos7[:3])
+    torch.manual_seed(5)
+    score, loss = test_epoch(fwd, loader, metric, loss_fn)
+    assert abs(score - ref_score) <= 1e-5 * max(1.0, abs(ref_score))
+    assert abs(float(loss) - float(ref_loss)) <= 1e-6 * max(1.0, abs(float(ref_loss)))
+
+
 def test_edge_cases_single_subgraph_empty_rows_and_tiny_graph():
     """B = 1, a one-node subgraph, an all-padding row in the middle, and a 3-node graph."""
     import functools

@@ -121,3 +121,24 @@ def test_synthetic_shapes_small():
     e = datasets.powerlaw_edges(2000, 8000, 0)
     deg = torch.bincount(torch.cat((e[0], e[1])), minlength=2000)
     assert e.shape == (2, 8000) and deg.max() > 20 * deg.float().mean()
+
+
+def test_epoch_batches_follow_the_dataloader_order():
+    """index_batches / epoch_batches draw from torch's RNG exactly like torch.utils.data.DataLoader, so the
+    captured-step epoch loop sees the same seeded subgraph order as `for batch in loader`."""
+    from glass_b200 import SubGDataset
+    n = 23
+    ds = SubGDataset.GDataset(torch.zeros(5, 1), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0),
+                              torch.arange(n * 4).reshape(n, 4), torch.arange(n))
+    for shuffle, drop_last in ((True, True), (True, False), (False, False)):
+        loader = SubGDataset.GDataloader(ds, batch_size=5, shuffle=shuffle, drop_last=drop_last)
+        torch.manual_seed(11)
+        ref = [(b[3].clone(), b[4].clone()) for _ in range(2) for b in loader]          # two epochs
+        after_ref = torch.rand(1)
+        torch.manual_seed(11)
+        got = [(p.clone(), y.clone()) for _ in range(2) for p, y in SubGDataset.epoch_batches(loader)]
+        after_got = torch.rand(1)
+        assert len(ref) == len(got) == 2 * (n // 5 if drop_last else -(-n // 5))
+        for (rp, ry), (gp, gy) in zip(ref, got):
+            assert torch.equal(rp, gp) and torch.equal(ry, gy)
+        assert torch.equal(after_ref, after_got)                                         # same RNG consumption
