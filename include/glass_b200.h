@@ -70,7 +70,10 @@ int glass_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t
 
 /* ------------------------------------------------------------------------------------------
  * adj @ x  (impl/models.py:164; backward = the same kernel on the transposed CSR)
- * y[r, :] = sum_{e in row r} val[e] * x[col[e], :]  accumulated in CSR order (deterministic).
+ * y[r, :] = sum_{e in row r} val[e] * x[col[e], :]  (deterministic: fixed summation order per shape).
+ * Graphs that fill the GPU (n_rows * 32 lanes > about two waves): one fp32 FMA chain per output in CSR
+ * order, bit-equal to a sequential CPU loop.  Smaller graphs: 32/G neighbour slots per row (G = h/4
+ * feature lanes), slot s adds every (32/G)-th entry, the slot sums are added by a fixed butterfly.
  * n_rows = rows of the CSR block; n_cols = rows of x (every column index must be < n_cols).
  * ------------------------------------------------------------------------------------------ */
 int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
