@@ -42,10 +42,35 @@ def _block(rowptr, col, val, lo, hi, remap):
     return rp, c, val[s:e].contiguous()
 
 
-class RowPartitionedAdj:
-    """This rank's row blocks of A and A^T with columns remapped to the padded all-gather layout."""
+def _split_columns(rp, c, v, lo_col: int, hi_col: int):
+    """Split a CSR block into the entries whose column lies in [lo_col, hi_col) -- re-based to 0, they index
+    this rank's own feature shard -- and the rest (columns unchanged).  Entry order inside a row is kept."""
+    n_rows = rp.numel() - 1
+    counts = (rp[1:] - rp[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=c.device), counts)
+    own = (c >= lo_col) & (c < hi_col)
 
-    def __init__(self, adj: ops.CSRAdj, rank: int, world: int, group=None):
+    def pick(sel, shift):
+        cnt = torch.bincount(rows[sel], minlength=n_rows)
+        rp_new = torch.zeros(n_rows + 1, dtype=torch.int64, device=c.device)
+        torch.cumsum(cnt, 0, out=rp_new[1:])
+        return rp_new.to(torch.int32), (c[sel] - shift).contiguous(), v[sel].contiguous()
+
+    return pick(own, lo_col), pick(~own, 0)
+
+
+class RowPartitionedAdj:
+    """This rank's row blocks of A and A^T with columns remapped to the padded all-gather layout.
+
+    overlap=True additionally splits each block by column ownership: the entries that touch this rank's own
+    feature rows are multiplied while the all-gather is in flight, the remote ones afterwards (SURVEY.md
+    section 8e "start SpMM on locally-owned columns first").  The two partial products are added, so the
+    summation order differs from the replicated SpMM (last-bit differences); overlap=False is bit-identical.
+    A kernel that gathers straight from peer memory instead is the wrong trade here: peer loads bypass the
+    local L2, so every remote entry would pull its 256-byte row over NVLink (12.8 GB per SpMM at N = 2 on the
+    stress graph) against 256 MB for the all-gather."""
+
+    def __init__(self, adj: ops.CSRAdj, rank: int, world: int, group=None, overlap: bool = False):
         self.rank, self.world, self.group, self.n = rank, world, group, adj.n
         dev = adj.col.device
         self.bounds = balanced_row_splits(adj.rowptr, world)
@@ -64,24 +89,48 @@ class RowPartitionedAdj:
         self.local.make_plans()
         self.nnz_local = int(blk[1].numel())
         self.gather_override = None     # tests: callable(padded_local) -> [world * pad, H] without a process group
+        self.own = self.rem = None
+        if overlap:
+            lo_col = rank * self.pad
+            (o, r), (ot, rt) = _split_columns(*blk, lo_col, lo_col + self.rows), _split_columns(*blk_t, lo_col, lo_col + self.rows)
+            self.own = ops.CSRAdj(self.rows, *o, *ot, none, adj.aggr).make_plans()
+            self.rem = ops.CSRAdj(self.rows, *r, *rt, none, adj.aggr).make_plans()
 
     def shard(self, full: torch.Tensor) -> torch.Tensor:
         """Rows of a replicated [N, H] matrix owned by this rank."""
         return full[self.lo:self.hi].contiguous()
 
-    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+    def _gather_async(self, local: torch.Tensor):
+        """Start the all-gather; returns (gathered buffer, wait()) -- wait() orders the current stream after it."""
         h = local.shape[1]
         send = local
         if self.rows != self.pad:
             send = torch.zeros((self.pad, h), dtype=local.dtype, device=local.device)
             send[:self.rows] = local
+        send = send.contiguous()
         if self.gather_override is not None:
-            return self.gather_override(send.contiguous())
+            out = self.gather_override(send)
+            return out, (lambda: None)
         out = torch.empty((self.world * self.pad, h), dtype=local.dtype, device=local.device)
         if self.world > 1:
-            dist.all_gather_into_tensor(out, send.contiguous(), group=self.group)
-        else:
-            out.copy_(send)
+            work = dist.all_gather_into_tensor(out, send, group=self.group, async_op=True)
+            return out, work.wait
+        out.copy_(send)
+        return out, (lambda: None)
+
+    def _spmm_overlapped(self, v_local: torch.Tensor, transposed: bool) -> torch.Tensor:
+        full, wait = self._gather_async(v_local)
+        own, rem = (self.own.t(), self.rem.t()) if transposed else (self.own, self.rem)
+        y = torch.empty((self.rows, v_local.shape[1]), dtype=torch.float32, device=v_local.device)
+        ops._run_spmm(own.rowptr, own.col, own.val, own.plan, v_local.contiguous(), y)      # overlaps the gather
+        wait()
+        y2 = torch.empty_like(y)
+        ops._run_spmm(rem.rowptr, rem.col, rem.val, rem.plan, full, y2)
+        return y.add_(y2)
+
+    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        out, wait = self._gather_async(local)
+        wait()
         return out
 
     def spmm(self, x_local: torch.Tensor) -> torch.Tensor:
@@ -93,6 +142,8 @@ class _PartSpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, part: RowPartitionedAdj):
         ctx.part = part
+        if part.own is not None:
+            return part._spmm_overlapped(x_local, False)
         x_full = part._gather(x_local)
         y = torch.empty((part.rows, x_local.shape[1]), dtype=torch.float32, device=x_local.device)
         a = part.local
@@ -102,6 +153,8 @@ class _PartSpMM(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         part = ctx.part
+        if part.own is not None:
+            return part._spmm_overlapped(gy.contiguous(), True), None
         gy_full = part._gather(gy.contiguous())
         gx = torch.empty((part.rows, gy.shape[1]), dtype=torch.float32, device=gy.device)
         a = part.local

@@ -410,9 +410,11 @@ def test_labels_and_pad2batch_known_answers():
 
 
 # ------------------------------------------------------------------------------------------ row partitioning
+@pytest.mark.parametrize("overlap", [False, True])
 @pytest.mark.parametrize("world", [1, 3, 4])
-def test_row_partitioned_spmm_single_device_emulation(world):
-    """All ranks' blocks built on one GPU; the all-gather is emulated by concatenating the padded shards."""
+def test_row_partitioned_spmm_single_device_emulation(world, overlap):
+    """All ranks' blocks built on one GPU; the all-gather is emulated by concatenating the padded shards.
+    overlap=True multiplies the locally-owned columns first (while the gather would be in flight)."""
     from glass_b200 import datasets, ops
     from glass_b200.partition import RowPartitionedAdj
     n, h = 6000, 64
@@ -424,8 +426,10 @@ def test_row_partitioned_spmm_single_device_emulation(world):
     xf = x.clone().requires_grad_(True)
     y_ref = ops.spmm(adj, xf)
     y_ref.backward(gy)
-    parts = [RowPartitionedAdj(adj, r, world) for r in range(world)]
+    parts = [RowPartitionedAdj(adj, r, world, overlap=overlap) for r in range(world)]
     nnz = [p.nnz_local for p in parts]
+    if overlap:
+        assert all(p.own.nnz + p.rem.nnz == p.nnz_local for p in parts)
     assert sum(nnz) == adj.nnz and max(nnz) <= 1.3 * adj.nnz / world + 4096      # balanced by entries
     pad = parts[0].pad
 
