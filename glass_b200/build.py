@@ -6,6 +6,7 @@ The library has no Python/torch dependency: plain C ABI (include/glass_b200.h), 
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
@@ -41,12 +42,25 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _up_to_date(stamp: str, dig: str) -> bool:
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     stamp = os.path.join(OBJ_DIR, "stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and _up_to_date(stamp, dig):
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time: under torchrun every rank calls build(); the others wait and find the stamp
+    with open(os.path.join(OBJ_DIR, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _up_to_date(stamp, dig):
+            return LIB
+        return _build_locked(stamp, dig, verbose)
+
+
+def _build_locked(stamp: str, dig: str, verbose: bool) -> str:
     nvcc = _nvcc()
 
     def compile_one(src):
@@ -62,10 +76,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
+    tmp = LIB + ".tmp"
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs,
                         "-cudart", "static"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)        # atomic: a process that already mapped the old file keeps its inode
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB
