@@ -1,37 +1,40 @@
-"""impl/train.py equivalents: one training epoch and one evaluation pass over a loader."""
+"""Epoch drivers with the call signatures of impl/train.py (train :4-17, test :20-34).
+
+A loader batch is a tuple whose last element is the target and whose other elements are the positional
+arguments of the model (impl/SubGDataset.py:92-96).  The captured-graph equivalents live in graphed.py
+(train_epoch / test_epoch); these eager versions are what `GLASSTest.py` uses without --graph.
+"""
 from __future__ import annotations
 
 import torch
 
 
 def train(optimizer, model, dataloader, loss_fn, sync_each_step: bool = True):
-    """impl/train.py:4-17: mean loss over the epoch; one optimizer step per batch.
+    """One optimizer step per batch; returns the mean of the per-batch losses (impl/train.py:17).
 
-    sync_each_step=True reads the loss back every step exactly like the reference (`.item()`,
-    impl/train.py:15 -- one host sync per step); False defers the read to the end of the epoch
-    (same values, no per-step sync)."""
+    sync_each_step=True reads every loss back right away, which is what the reference's `.item()`
+    (impl/train.py:15) does: one host sync per step.  False keeps the losses on the device until the
+    epoch ends -- same value, no per-step sync."""
     model.train()
-    losses = []
-    for batch in dataloader:
+    history = []
+    for *inputs, target in dataloader:
         optimizer.zero_grad()
-        pred = model(*batch[:-1], id=0)
-        loss = loss_fn(pred, batch[-1])
-        loss.backward()
-        losses.append(loss.detach().item() if sync_each_step else loss.detach())
+        step_loss = loss_fn(model(*inputs, id=0), target)
+        step_loss.backward()
         optimizer.step()
+        history.append(step_loss.detach())
+        if sync_each_step:
+            history[-1] = history[-1].item()
     if sync_each_step:
-        return sum(losses) / len(losses)
-    return float(torch.stack(losses).double().sum().item()) / len(losses)
+        return sum(history) / len(history)
+    return float(torch.stack(history).double().sum().item()) / len(history)
 
 
 @torch.no_grad()
 def test(model, dataloader, metrics, loss_fn):
-    """impl/train.py:20-34: score and loss over all batches of the loader."""
+    """(metrics(logits, targets), loss_fn(logits, targets)) over the whole loader, eval mode (impl/train.py:34)."""
     model.eval()
-    preds, ys = [], []
-    for batch in dataloader:
-        preds.append(model(*batch[:-1]))
-        ys.append(batch[-1])
-    pred = torch.cat(preds, dim=0)
-    y = torch.cat(ys, dim=0)
-    return metrics(pred.cpu().numpy(), y.cpu().numpy()), loss_fn(pred, y)
+    pairs = [(model(*inputs), target) for *inputs, target in dataloader]
+    logits = torch.cat([out for out, _ in pairs], dim=0)
+    targets = torch.cat([t for _, t in pairs], dim=0)
+    return metrics(logits.cpu().numpy(), targets.cpu().numpy()), loss_fn(logits, targets)

@@ -142,3 +142,42 @@ def test_epoch_batches_follow_the_dataloader_order():
         for (rp, ry), (gp, gy) in zip(ref, got):
             assert torch.equal(rp, gp) and torch.equal(ry, gy)
         assert torch.equal(after_ref, after_got)                                         # same RNG consumption
+
+
+def test_train_and_test_epoch_drivers_follow_the_reference_loop():
+    """glass_b200.train.{train,test} against a hand-written loop on a plain torch module (host logic only)."""
+    from glass_b200 import train
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(3, 2)
+
+        def forward(self, a, b, id=0):
+            return self.lin(a + b)
+
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.randint(0, 2, (n,), generator=g))
+               for n in (4, 4, 3)]
+    loss_fn = torch.nn.CrossEntropyLoss()
+    results = []
+    for sync in (True, False, None):
+        torch.manual_seed(1)
+        m = Tiny()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+        if sync is None:                                   # the loop of impl/train.py:8-17, written out
+            m.train()
+            losses = []
+            for a, b, y in batches:
+                opt.zero_grad()
+                loss = loss_fn(m(a, b, id=0), y)
+                loss.backward()
+                losses.append(loss.item())
+                opt.step()
+            mean = sum(losses) / len(losses)
+        else:
+            mean = train.train(opt, m, batches, loss_fn, sync_each_step=sync)
+        score, loss = train.test(m, batches, lambda p, t: float((p.argmax(-1) == t).mean()), loss_fn)
+        results.append((mean, score, float(loss)))
+    for r in results[:2]:
+        assert abs(r[0] - results[2][0]) < 1e-6 and r[1] == results[2][1] and abs(r[2] - results[2][2]) < 1e-6
