@@ -1,100 +1,112 @@
-"""impl/SubGDataset.py equivalents: split container and the batch loaders that feed train/test.
+"""Split container and batch loaders with the public names of impl/SubGDataset.py.
 
-A batch is the tuple (x, edge_index, edge_attr, subG_node[perm], z, y[perm]) (impl/SubGDataset.py:92-96):
-the whole base graph plus the padded node sets, labels z and targets of the sampled subgraphs.
-Index sampling goes through torch.utils.data.DataLoader exactly like the reference, so a seeded run
-draws the same permutations.
+A batch is `(x, edge_index, edge_attr, subG_node[idx], [z,] y[idx])` (impl/SubGDataset.py:92-96): the whole
+base graph by reference plus the padded node sets and targets of the sampled subgraphs.  The loaders here
+are plain iterables built on torch's samplers; they draw from torch's global RNG in exactly the order
+`torch.utils.data.DataLoader` does (the reference subclasses it), so a seeded run samples the same
+subgraphs in the same order -- `tests/test_host_logic.py` pins that against DataLoader itself.
 """
 from __future__ import annotations
 
+from typing import Callable, Iterator, Tuple
+
 import torch
-from torch.utils.data import DataLoader
+from torch.utils.data import BatchSampler, RandomSampler, SequentialSampler
+
+_FIELDS = ("x", "edge_index", "edge_attr", "pos", "y")
 
 
 class GDataset:
+    """One split: base graph (x, edge_index, edge_attr) + padded subgraph node sets `pos` [S, Lmax] (-1 = pad)
+    + targets `y` [S]  (impl/SubGDataset.py:6-36)."""
+
     def __init__(self, x, edge_index, edge_attr, pos, y):
-        self.x, self.edge_index, self.edge_attr, self.pos, self.y = x, edge_index, edge_attr, pos, y
+        for name, value in zip(_FIELDS, (x, edge_index, edge_attr, pos, y)):
+            setattr(self, name, value)
         self.num_nodes = x.shape[0]
 
-    def __len__(self):
+    def __len__(self) -> int:
         return self.pos.shape[0]
 
     def __getitem__(self, idx):
         return self.pos[idx], self.y[idx]
 
     def to(self, device):
-        for name in ("x", "edge_index", "edge_attr", "pos", "y"):
+        for name in _FIELDS:
             setattr(self, name, getattr(self, name).to(device))
         return self
 
 
-class GDataloader(DataLoader):
-    def __init__(self, Gdataset, batch_size=64, shuffle=True, drop_last=False):
-        super().__init__(torch.arange(len(Gdataset)).to(Gdataset.x.device), batch_size=batch_size, shuffle=shuffle,
-                         drop_last=drop_last)
-        self.Gdataset = Gdataset
+def _zero_labels(x, pos):
+    return torch.zeros((x.shape[0], x.shape[1]), dtype=torch.int64)
 
-    def get_x(self):
-        return self.Gdataset.x
 
-    def get_ei(self):
-        return self.Gdataset.edge_index
+class GDataloader:
+    """Iterable over the subgraph batches of a GDataset (impl/SubGDataset.py:38-73).
 
-    def get_ea(self):
-        return self.Gdataset.edge_attr
+    `generator=None` means torch's global RNG, like DataLoader's default."""
 
-    def get_pos(self):
-        return self.Gdataset.pos
+    def __init__(self, Gdataset: GDataset, batch_size: int = 64, shuffle: bool = True, drop_last: bool = False,
+                 generator=None):
+        self.Gdataset, self.batch_size, self.generator = Gdataset, batch_size, generator
+        ids = range(len(Gdataset))
+        sampler = RandomSampler(ids, generator=generator) if shuffle else SequentialSampler(ids)
+        self.batch_sampler = BatchSampler(sampler, batch_size, drop_last)
 
-    def get_y(self):
-        return self.Gdataset.y
+    def __len__(self) -> int:
+        return len(self.batch_sampler)
+
+    def index_batches(self) -> Iterator[torch.Tensor]:
+        """CPU int64 index batches of one epoch.  RNG order of DataLoader: the iterator's base seed is drawn
+        when iteration starts, the RandomSampler's own seed when the first index is requested."""
+        torch.empty((), dtype=torch.int64).random_(generator=self.generator)
+        for idx in self.batch_sampler:
+            yield torch.as_tensor(idx, dtype=torch.int64)
+
+    def _batch(self, pos, y) -> Tuple:
+        ds = self.Gdataset
+        return ds.x, ds.edge_index, ds.edge_attr, pos, y
 
     def __iter__(self):
-        self.iter = super().__iter__()
-        return self
+        ds = self.Gdataset
+        for idx in self.index_batches():
+            idx = idx.to(ds.pos.device)
+            yield self._batch(ds.pos[idx], ds.y[idx])
 
-    def __next__(self):
-        perm = next(self.iter)
-        return self.get_x(), self.get_ei(), self.get_ea(), self.get_pos()[perm], self.get_y()[perm]
+
+# accessor methods of the reference loader (impl/SubGDataset.py:50-63)
+for _method, _field in zip(("get_x", "get_ei", "get_ea", "get_pos", "get_y"), _FIELDS):
+    setattr(GDataloader, _method, (lambda field: lambda self: getattr(self.Gdataset, field))(_field))
 
 
 class ZGDataloader(GDataloader):
-    """Adds the per-batch node labels z = z_fn(x, subG_node[perm]) (MaxZOZ for --use_maxzeroone)."""
+    """Adds the per-batch node labels z = z_fn(x, subG_node[idx]) before the target (impl/SubGDataset.py:76-96);
+    `utils.MaxZOZ` for --use_maxzeroone, all-zero labels by default."""
 
-    def __init__(self, Gdataset, batch_size=64, shuffle=True, drop_last=False,
-                 z_fn=lambda x, y: torch.zeros((x.shape[0], x.shape[1]), dtype=torch.int64)):
-        super().__init__(Gdataset, batch_size, shuffle, drop_last)
+    def __init__(self, Gdataset: GDataset, batch_size: int = 64, shuffle: bool = True, drop_last: bool = False,
+                 z_fn: Callable = _zero_labels, generator=None):
+        super().__init__(Gdataset, batch_size, shuffle, drop_last, generator)
         self.z_fn = z_fn
 
-    def __next__(self):
-        perm = next(self.iter)
-        tpos = self.get_pos()[perm]
-        return self.get_x(), self.get_ei(), self.get_ea(), tpos, self.z_fn(self.get_x(), tpos), self.get_y()[perm]
+    def _batch(self, pos, y) -> Tuple:
+        ds = self.Gdataset
+        return ds.x, ds.edge_index, ds.edge_attr, pos, self.z_fn(ds.x, pos), y
 
 
-def index_batches(loader: GDataloader):
-    """The index batches `iter(loader)` would produce, as CPU int64 tensors, drawing from torch's global RNG
-    in the same order as torch.utils.data.DataLoader does (the iterator's base seed first, then the
-    RandomSampler's own seed on its first draw), so a seeded run sees the same subgraph order whichever
-    way the epoch is iterated.  tests/test_host_logic.py pins this against DataLoader itself."""
-    if loader.generator is None:
-        torch.empty((), dtype=torch.int64).random_()          # _BaseDataLoaderIter.__init__: self._base_seed
-    else:
-        torch.empty((), dtype=torch.int64).random_(generator=loader.generator)
-    for idx in loader.batch_sampler:
-        yield torch.as_tensor(idx, dtype=torch.int64)
+def index_batches(loader: GDataloader) -> Iterator[torch.Tensor]:
+    return loader.index_batches()
 
 
 def epoch_batches(loader: GDataloader):
     """(subG_node, y) of every batch of one epoch in the loader's order, for the captured train / eval
     steps: one gather of the whole epoch instead of one per batch, no per-batch z_fn (the captured step
-    computes the labels itself), no per-batch collation of device scalars."""
-    batches = list(index_batches(loader))
+    computes the labels itself)."""
+    batches = list(loader.index_batches())
     if not batches:
         return
-    pos, y = loader.get_pos(), loader.get_y()
-    order = torch.cat(batches).to(pos.device, non_blocking=True)
-    pos_e, y_e = pos[order], y[order]
+    ds = loader.Gdataset
+    order = torch.cat(batches).to(ds.pos.device, non_blocking=True)
+    pos_e, y_e = ds.pos[order], ds.y[order]
     off = 0
     for b in batches:
         n = b.numel()

@@ -123,25 +123,33 @@ def test_synthetic_shapes_small():
     assert e.shape == (2, 8000) and deg.max() > 20 * deg.float().mean()
 
 
-def test_epoch_batches_follow_the_dataloader_order():
-    """index_batches / epoch_batches draw from torch's RNG exactly like torch.utils.data.DataLoader, so the
-    captured-step epoch loop sees the same seeded subgraph order as `for batch in loader`."""
+def test_loaders_follow_the_torch_dataloader_order():
+    """GDataloader / epoch_batches draw from torch's RNG exactly like the torch.utils.data.DataLoader the
+    reference subclasses (impl/SubGDataset.py:38-47): same index batches, same RNG state afterwards."""
+    from torch.utils.data import DataLoader
     from glass_b200 import SubGDataset
     n = 23
     ds = SubGDataset.GDataset(torch.zeros(5, 1), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0),
                               torch.arange(n * 4).reshape(n, 4), torch.arange(n))
     for shuffle, drop_last in ((True, True), (True, False), (False, False)):
-        loader = SubGDataset.GDataloader(ds, batch_size=5, shuffle=shuffle, drop_last=drop_last)
+        ref_loader = DataLoader(torch.arange(n), batch_size=5, shuffle=shuffle, drop_last=drop_last)
+        loader = SubGDataset.ZGDataloader(ds, batch_size=5, shuffle=shuffle, drop_last=drop_last)
+        assert len(loader) == len(ref_loader)
         torch.manual_seed(11)
-        ref = [(b[3].clone(), b[4].clone()) for _ in range(2) for b in loader]          # two epochs
+        ref = [(ds.pos[idx], ds.y[idx]) for _ in range(2) for idx in ref_loader]            # two epochs
         after_ref = torch.rand(1)
         torch.manual_seed(11)
-        got = [(p.clone(), y.clone()) for _ in range(2) for p, y in SubGDataset.epoch_batches(loader)]
-        after_got = torch.rand(1)
-        assert len(ref) == len(got) == 2 * (n // 5 if drop_last else -(-n // 5))
-        for (rp, ry), (gp, gy) in zip(ref, got):
-            assert torch.equal(rp, gp) and torch.equal(ry, gy)
-        assert torch.equal(after_ref, after_got)                                         # same RNG consumption
+        via_iter = [(b[3], b[-1]) for _ in range(2) for b in loader]
+        after_iter = torch.rand(1)
+        torch.manual_seed(11)
+        via_epoch = [(p, y) for _ in range(2) for p, y in SubGDataset.epoch_batches(loader)]
+        after_epoch = torch.rand(1)
+        assert len(ref) == len(via_iter) == len(via_epoch) == 2 * (n // 5 if drop_last else -(-n // 5))
+        for (rp, ry), (ip, iy), (ep, ey) in zip(ref, via_iter, via_epoch):
+            assert torch.equal(rp, ip) and torch.equal(ry, iy) and torch.equal(rp, ep) and torch.equal(ry, ey)
+        assert torch.equal(after_ref, after_iter) and torch.equal(after_ref, after_epoch)   # same RNG consumption
+    b = next(iter(SubGDataset.ZGDataloader(ds, 4, shuffle=False)))
+    assert len(b) == 6 and b[4].shape == (5, 1) and b[4].dtype == torch.int64 and loader.get_pos() is ds.pos
 
 
 def test_train_and_test_epoch_drivers_follow_the_reference_loop():
