@@ -91,23 +91,19 @@ class GLASSConv(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, activation=nn.ReLU(inplace=True), aggr="mean",
                  z_ratio=0.8, dropout=0.2):
         super().__init__()
-        self.trans_fns = nn.ModuleList([nn.Linear(in_channels, out_channels), nn.Linear(in_channels, out_channels)])
-        self.comb_fns = nn.ModuleList([nn.Linear(in_channels + out_channels, out_channels),
-                                       nn.Linear(in_channels + out_channels, out_channels)])
-        self.adj = None
-        self.activation = activation
-        self.aggr = aggr
+        # creation order fixes both the state_dict layout and the seeded initial values: W0, W1 of the
+        # transform, W0, W1 of the combine (input = [aggregated | x_]), then the norm
+        wide = in_channels + out_channels
+        self.trans_fns = nn.ModuleList(nn.Linear(in_channels, out_channels) for _ in range(2))
+        self.comb_fns = nn.ModuleList(nn.Linear(wide, out_channels) for _ in range(2))
         self.gn = GraphNorm(out_channels)
-        self.z_ratio = z_ratio
+        self.activation, self.aggr, self.z_ratio, self.dropout = activation, aggr, z_ratio, dropout
+        self.adj = None                     # CSRAdj, built on the first forward and kept (impl/models.py:154-156)
         self.reset_parameters()
-        self.dropout = dropout
 
     def reset_parameters(self):
-        for lin in self.trans_fns:
-            lin.reset_parameters()
-        for lin in self.comb_fns:
-            lin.reset_parameters()
-        self.gn.reset_parameters()
+        for module in (*self.trans_fns, *self.comb_fns, self.gn):
+            module.reset_parameters()
 
     def forward(self, x_, edge_index, edge_weight, mask):
         if self.adj is None:  # cached on first use, like impl/models.py:154-156
@@ -130,37 +126,22 @@ class EmbZGConv(nn.Module):
     def __init__(self, hidden_channels, output_channels, num_layers, max_deg, dropout=0, activation=nn.ReLU(),
                  conv=GLASSConv, gn=True, jk=False, **kwargs):
         super().__init__()
+        out_widths = [hidden_channels] * (num_layers - 1) + [output_channels]       # per conv layer
         self.input_emb = nn.Embedding(max_deg + 1, hidden_channels, scale_grad_by_freq=False)
         self.emb_gn = GraphNorm(hidden_channels)
-        self.convs = nn.ModuleList()
-        self.jk = jk
-        for _ in range(num_layers - 1):
-            self.convs.append(conv(in_channels=hidden_channels, out_channels=hidden_channels, activation=activation,
-                                   **kwargs))
-        self.convs.append(conv(in_channels=hidden_channels, out_channels=output_channels, activation=activation,
-                               **kwargs))
-        self.activation = activation
-        self.dropout = dropout
-        if gn:
-            self.gns = nn.ModuleList()
-            for _ in range(num_layers - 1):
-                self.gns.append(GraphNorm(hidden_channels))
-            if self.jk:
-                self.gns.append(GraphNorm(output_channels + (num_layers - 1) * hidden_channels))
-            else:
-                self.gns.append(GraphNorm(output_channels))
+        self.convs = nn.ModuleList(conv(in_channels=hidden_channels, out_channels=w, activation=activation, **kwargs)
+                                   for w in out_widths)
+        self.jk, self.activation, self.dropout = jk, activation, dropout
+        if gn:   # one norm after every layer; the last one spans the JK concat when jk is set
+            norm_widths = out_widths[:-1] + [sum(out_widths) if jk else output_channels]
+            self.gns = nn.ModuleList(GraphNorm(w) for w in norm_widths)
         else:
             self.gns = None
         self.reset_parameters()
 
     def reset_parameters(self):
-        self.input_emb.reset_parameters()
-        self.emb_gn.reset_parameters()
-        for conv in self.convs:
-            conv.reset_parameters()
-        if self.gns is not None:
-            for gn in self.gns:
-                gn.reset_parameters()
+        for module in (self.input_emb, self.emb_gn, *self.convs, *(self.gns or ())):
+            module.reset_parameters()
 
     def _identity_lookup(self, ids: torch.Tensor) -> bool:
         """--use_nodeid: ids == arange(N) and the table has N rows, so the lookup (impl/models.py:248) is the
@@ -240,19 +221,16 @@ class PoolModule(nn.Module):
         return ops.segment_pool(emb, subG_node, self.padded_mode())
 
 
-class AddPool(PoolModule):
+def _pool_class(name: str, pool_fn):
+    """AddPool / MaxPool / MeanPool of impl/models.py:295-307: PoolModule with the pooling function bound."""
     def __init__(self, trans_fn=None):
-        super().__init__(global_add_pool, trans_fn)
+        PoolModule.__init__(self, pool_fn, trans_fn)
+    return type(name, (PoolModule,), {"__init__": __init__, "__module__": __name__})
 
 
-class MaxPool(PoolModule):
-    def __init__(self, trans_fn=None):
-        super().__init__(global_max_pool, trans_fn)
-
-
-class MeanPool(PoolModule):
-    def __init__(self, trans_fn=None):
-        super().__init__(global_mean_pool, trans_fn)
+AddPool = _pool_class("AddPool", global_add_pool)
+MaxPool = _pool_class("MaxPool", global_max_pool)
+MeanPool = _pool_class("MeanPool", global_mean_pool)
 
 
 class SizePool(AddPool):
@@ -270,22 +248,27 @@ class SizePool(AddPool):
         return ops.segment_pool_batch(x, batch, "size")
 
 
-class GLASS(nn.Module):
-    """impl/models.py:322-355."""
+class _SubgraphModel(nn.Module):
+    """Shared plumbing of GLASS and EdgeGNN: node embeddings -> pooled subgraph vectors -> prediction head `id`."""
 
-    def __init__(self, conv: EmbZGConv, preds: nn.ModuleList, pools: nn.ModuleList):
+    def __init__(self, conv, preds: nn.ModuleList, pools: nn.ModuleList):
         super().__init__()
-        self.conv = conv
-        self.preds = preds
-        self.pools = pools
+        self.conv, self.preds, self.pools = conv, preds, pools
 
     def NodeEmb(self, x, edge_index, edge_weight, z=None):
-        embs = []
-        for c in range(x.shape[1]):                                                         # :338
-            embs.append(self.conv(x[:, c, :].reshape(x.shape[0], x.shape[-1]), edge_index, edge_weight, z))
-        if len(embs) == 1:  # mean over a single feature copy (always the case on this path) is the identity
-            return embs[0]
-        return torch.mean(torch.stack(embs, dim=1), dim=1)                                  # :342-343
+        """impl/models.py:336-344: one pass per feature copy x[:, c, :] (always one copy on this path), averaged."""
+        n, copies, width = x.shape
+        embs = [self.conv(x[:, c, :].reshape(n, width), edge_index, edge_weight, z) for c in range(copies)]
+        # the mean over a single copy is the identity (bit for bit), so no kernel is spent on it
+        return embs[0] if copies == 1 else torch.mean(torch.stack(embs, dim=1), dim=1)
+
+    def forward(self, x, edge_index, edge_weight, subG_node, z=None, id=0):
+        pooled = self.Pool(self.NodeEmb(x, edge_index, edge_weight, z), subG_node, self.pools[id])
+        return self.preds[id](pooled)
+
+
+class GLASS(_SubgraphModel):
+    """impl/models.py:322-355."""
 
     def Pool(self, emb, subG_node, pool):
         mode = pool.padded_mode() if isinstance(pool, PoolModule) else None
@@ -293,11 +276,6 @@ class GLASS(nn.Module):
             return ops.segment_pool(emb, subG_node, mode)                                   # fused :347-349
         batch, pos = pad2batch(subG_node)                                                   # :347
         return pool(ops.embedding(pos, emb), batch)                                         # :348-349
-
-    def forward(self, x, edge_index, edge_weight, subG_node, z=None, id=0):
-        emb = self.NodeEmb(x, edge_index, edge_weight, z)
-        emb = self.Pool(emb, subG_node, self.pools[id])
-        return self.preds[id](emb)
 
 
 # --- plain (unlabeled) GNN used by the reference's link-prediction pre-training (GNNEmb.py) -----------
@@ -316,15 +294,12 @@ class MyGCNConv(nn.Module):
         super().__init__()
         self.trans_fn = nn.Linear(in_channels, out_channels)
         self.comb_fn = nn.Linear(in_channels + out_channels, out_channels)
-        self.adj = None
-        self.activation = activation
-        self.aggr = aggr
         self.gn = GraphNorm(out_channels)
+        self.activation, self.aggr, self.adj = activation, aggr, None
 
     def reset_parameters(self):
-        self.trans_fn.reset_parameters()
-        self.comb_fn.reset_parameters()
-        self.gn.reset_parameters()
+        for module in (self.trans_fn, self.comb_fn, self.gn):
+            module.reset_parameters()
 
     def forward(self, x_, edge_index, edge_weight):
         if self.adj is None:
@@ -342,32 +317,17 @@ class EmbGConv(nn.Module):
     def __init__(self, input_channels: int, hidden_channels: int, output_channels: int, num_layers: int, max_deg: int,
                  dropout=0, activation=nn.ReLU(inplace=True), conv=MyGCNConv, gn=True, jk=False, **kwargs):
         super().__init__()
+        # layer widths: input -> hidden -> ... -> hidden -> output (a single layer maps input -> output)
+        dims = [input_channels] + [hidden_channels] * (num_layers - 1) + [output_channels]
         self.input_emb = nn.Embedding(max_deg + 1, hidden_channels)
-        self.convs = nn.ModuleList()
-        self.jk = jk
-        if num_layers > 1:
-            self.convs.append(conv(in_channels=input_channels, out_channels=hidden_channels, **kwargs))
-            for _ in range(num_layers - 2):
-                self.convs.append(conv(in_channels=hidden_channels, out_channels=hidden_channels, **kwargs))
-            self.convs.append(conv(in_channels=hidden_channels, out_channels=output_channels, **kwargs))
-        else:
-            self.convs.append(conv(in_channels=input_channels, out_channels=output_channels, **kwargs))
-        self.activation = activation
-        self.dropout = dropout
-        if gn:
-            self.gns = nn.ModuleList()
-            for _ in range(num_layers - 1):
-                self.gns.append(GraphNorm(hidden_channels))
-        else:
-            self.gns = None
+        self.convs = nn.ModuleList(conv(in_channels=a, out_channels=b, **kwargs) for a, b in zip(dims, dims[1:]))
+        self.jk, self.activation, self.dropout = jk, activation, dropout
+        self.gns = nn.ModuleList(GraphNorm(hidden_channels) for _ in range(num_layers - 1)) if gn else None
         self.reset_parameters()
 
     def reset_parameters(self):
-        for conv in self.convs:
-            conv.reset_parameters()
-        if self.gns is not None:
-            for gn in self.gns:
-                gn.reset_parameters()
+        for module in (*self.convs, *(self.gns or ())):
+            module.reset_parameters()
 
     def forward(self, x, edge_index, edge_weight, z=None):
         import torch.nn.functional as F
@@ -384,24 +344,8 @@ class EmbGConv(nn.Module):
         return torch.cat(xs, dim=-1) if self.jk else xs[-1]
 
 
-class EdgeGNN(nn.Module):
+class EdgeGNN(_SubgraphModel):
     """impl/models.py:479-509: node embeddings -> mean of the two end points of each pair -> preds[id]."""
-
-    def __init__(self, conv, preds: nn.ModuleList, pools: nn.ModuleList):
-        super().__init__()
-        self.conv = conv
-        self.preds = preds
-        self.pools = pools
-
-    def NodeEmb(self, x, edge_index, edge_weight, z=None):
-        embs = [self.conv(x[:, c, :].reshape(x.shape[0], x.shape[-1]), edge_index, edge_weight, z)
-                for c in range(x.shape[1])]
-        return embs[0] if len(embs) == 1 else torch.mean(torch.stack(embs, dim=1), dim=1)
 
     def Pool(self, emb, subG_node, pool):
         return ops.segment_pool(emb, subG_node, "mean")      # emb[subG_node].mean(dim=1), impl/models.py:502-504
-
-    def forward(self, x, edge_index, edge_weight, subG_node, z=None, id=0):
-        emb = self.NodeEmb(x, edge_index, edge_weight, z)
-        emb = self.Pool(emb, subG_node, self.pools[id])
-        return self.preds[id](emb)

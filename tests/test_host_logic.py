@@ -189,3 +189,29 @@ def test_train_and_test_epoch_drivers_follow_the_reference_loop():
         results.append((mean, score, float(loss)))
     for r in results[:2]:
         assert abs(r[0] - results[2][0]) < 1e-6 and r[1] == results[2][1] and abs(r[2] - results[2][2]) < 1e-6
+
+
+def test_pretraining_modules_state_dict_layout_matches_reference_golden():
+    """EmbGConv / MyGCNConv / EdgeGNN are built with the reference's parameter names and order (CPU part of
+    tests/test_gpu_model.py::test_pretraining_modules_match_reference_golden)."""
+    import functools
+
+    import numpy as np
+    import torch.nn as nn
+
+    from glass_b200 import models
+    from tests.helpers import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "model_edgegnn.npz"))
+    H, L = 32, 2
+    conv = models.EmbGConv(H, H, H, L, max_deg=11, activation=nn.ReLU(inplace=True), jk=True, dropout=0.0,
+                           conv=functools.partial(models.MyGCNConv, aggr="mean", activation=nn.ReLU(inplace=True)), gn=True)
+    m = models.EdgeGNN(conv, nn.ModuleList([nn.Linear(H * L, 1)]), nn.ModuleList([models.MeanPool()]))
+    sd = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd.")}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    # pool wrappers keep the reference's class relations (impl/models.py:295-319)
+    assert issubclass(models.SizePool, models.AddPool) and issubclass(models.MaxPool, models.PoolModule)
+    assert models.MeanPool().padded_mode() == "mean" and models.SizePool().padded_mode() == "size"
+    assert models.AddPool(trans_fn=nn.Identity()).padded_mode() is None
+    one = models.EmbGConv(8, 16, 4, 1, max_deg=3)
+    assert [tuple(c.trans_fn.weight.shape) for c in one.convs] == [(4, 8)] and len(one.gns) == 0
