@@ -5,7 +5,7 @@
 
 A "step" is one training iteration of impl/train.py:10-16 (labels z, forward, loss, backward, optimizer)
 over one label batch on the whole base graph.  Default workload: the em_user-shaped synthetic graph with
-config/em_user.yml hyper-parameters (BASELINE.json configs[3], the roofline config).  Prints ONE JSON line
+the reference's em_user hyper-parameters (BASELINE.json configs[3], the roofline config).  Prints ONE JSON line
 (contract in the task statement): device-timed `value`, host-buffer `e2e`, the SpMM `roofline`, and the
 CPU `cpu_baseline` (oracle port of the reference modules, timed on this box's host cores).
 `--impl reference` times that CPU port alone with the same metric/config keys.

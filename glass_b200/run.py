@@ -1,5 +1,5 @@
 """Model / task construction mirroring GLASSTest.py (buildModel :129-175, loss & score :55-71,
-hyper-parameters from config/<dataset>.yml), for scripts, benchmarks and tests."""
+hyper-parameters of the reference's config/<dataset>.yml), for scripts, benchmarks and tests."""
 from __future__ import annotations
 
 import functools
@@ -13,14 +13,24 @@ import yaml
 from . import metrics, models
 
 _CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config")
-# which config/*.yml the synthetic shapes borrow their hyper-parameters from
+# which dataset's row the synthetic shapes borrow their hyper-parameters from
 CONFIG_OF = {"ppi_bp_shaped": "ppi_bp", "em_user_shaped": "em_user", "em_user_shaped_powerlaw": "em_user",
              "stress": "em_user", "stress_small": "em_user"}
 
 
 def load_params(dataset: str) -> dict:
-    with open(os.path.join(_CONFIG_DIR, f"{CONFIG_OF.get(dataset, dataset)}.yml")) as f:
-        return yaml.safe_load(f)
+    """Hyper-parameters of a dataset (GLASSTest.py:273-276).  A reference-style `config/<dataset>.yml` wins if
+    it exists; otherwise the row of `config/hparams.yml`, which holds the reference's values for all datasets."""
+    name = CONFIG_OF.get(dataset, dataset)
+    own = os.path.join(_CONFIG_DIR, f"{name}.yml")
+    if os.path.exists(own):
+        with open(own) as f:
+            return yaml.safe_load(f)
+    with open(os.path.join(_CONFIG_DIR, "hparams.yml")) as f:
+        table = yaml.safe_load(f)
+    if name not in table:
+        raise FileNotFoundError(f"no hyper-parameters for dataset {dataset!r} (config/hparams.yml or {own})")
+    return dict(table[name])
 
 
 def build_model(hidden_dim, conv_layer, dropout, jk, pool, z_ratio, aggr, max_deg, output_channels,
