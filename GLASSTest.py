@@ -70,13 +70,14 @@ class Experiment:
     def loader(self, ds, bs, shuffle=True, drop_last=True):
         if self.args.use_maxzeroone:
             return SubGDataset.ZGDataloader(ds, bs, z_fn=utils.MaxZOZ, shuffle=shuffle, drop_last=drop_last)
-        return SubGDataset.GDataloader(ds, bs, shuffle=shuffle, drop_last=drop_last)
+        # reference GLASSTest.py:122-126: without max-zero-one labels both loaders are GDataloader(ds, bs[, shuffle=True]),
+        # i.e. shuffled and drop_last=False -- the last short batch is kept, unlike the ZGDataloader path
+        return SubGDataset.GDataloader(ds, bs, shuffle=True, drop_last=False)
 
     def build_model(self, hidden_dim, conv_layer, dropout, jk, pool, z_ratio, aggr):
         table = None
         if self.args.use_nodeid:
-            print("synthetic stand-in for ", f"./Emb/{self.args.dataset}_{hidden_dim}.pt")
-            table = datasets.synthetic_embedding(self.n_node, hidden_dim, seed=0)
+            table = datasets.pretrained_embedding(self.args.dataset, hidden_dim, self.n_node, seed=0)
         return run.build_model(hidden_dim, conv_layer, dropout, jk, pool, z_ratio, aggr, self.max_deg, self.out_dim,
                                pretrained=table, device=self.device)
 

@@ -24,6 +24,10 @@ class GDataset:
         for name, value in zip(_FIELDS, (x, edge_index, edge_attr, pos, y)):
             setattr(self, name, value)
         self.num_nodes = x.shape[0]
+        # the reference fails with an index error when a subgraph names a node outside the graph (emb[pos],
+        # impl/models.py:348); the pooling / label kernels skip such ids, so the split is checked once here
+        if pos.numel() and (int(pos.max()) >= self.num_nodes or int(pos.min()) < -1):
+            raise IndexError(f"subG_node holds node ids outside [-1, {self.num_nodes})")
 
     def __len__(self) -> int:
         return self.pos.shape[0]

@@ -229,4 +229,84 @@ def load_dataset(name: str, seed: Optional[int] = None, device=None) -> "BaseGra
         return BaseGraph(torch.empty((n, 1, 0)), e, torch.ones(e.shape[1]), pad, label, mask)
     if name in _SHAPES:
         return synthetic_graph(name, 0 if seed is None else seed, device)
+    if name in REAL:
+        return load_real_dataset(name)
     raise NotImplementedError(name)
+
+
+REAL = ("ppi_bp", "hpo_metab", "hpo_neuro", "em_user")
+
+
+def real_dataset_dir(name: str) -> str:
+    """./dataset/<name> like the reference (datasets.py:180-222, CWD-relative); GLASS_DATASET_DIR overrides the root."""
+    return os.path.join(os.environ.get("GLASS_DATASET_DIR", "./dataset"), name)
+
+
+def parse_subgraph_file(path: str):
+    """SubGNN `subgraphs.pth` text format (datasets.py:131-174): one subgraph per line,
+    `n1-n2-...<TAB>label[-label...]<TAB>train|val|test`.  Label names get ids in order of first appearance;
+    more than one label on any line makes the task multi-label.  Returns
+    ({split: (node lists, label-id lists)}, multilabel)."""
+    label_id = {}
+    splits = {"train": ([], []), "val": ([], []), "test": ([], [])}
+    multilabel = False
+    with open(path) as f:
+        for line in f:
+            fields = line.split("\t")
+            nodes = [int(tok) for tok in fields[0].split("-") if tok != ""]
+            if not nodes:
+                continue
+            names = fields[1].split("-")
+            multilabel = multilabel or len(names) > 1
+            for nm in names:
+                label_id.setdefault(nm, len(label_id))
+            split = fields[2].strip()
+            if split in splits:
+                splits[split][0].append(nodes)
+                splits[split][1].append([label_id[nm] for nm in names])
+    return splits, multilabel
+
+
+def load_real_dataset(name: str) -> "BaseGraph":
+    """datasets.py:127-227 for ppi_bp / hpo_metab / hpo_neuro / em_user (files are not shipped with the
+    reference: README.md:26 gives a download link).  Same conventions: validation and test splits swap when the
+    validation split is the smaller one (:168-171), mask 0/1/2 in train/val/test order, single-label targets as
+    a float vector, multi-label targets as a float indicator matrix, node count = 1 + largest id seen."""
+    root = real_dataset_dir(name)
+    sub_path, edge_path = os.path.join(root, "subgraphs.pth"), os.path.join(root, "edge_list.txt")
+    if not (os.path.exists(sub_path) and os.path.exists(edge_path)):
+        raise FileNotFoundError(f"{name}: expected {sub_path} and {edge_path} (download link in the reference's "
+                                f"README; set GLASS_DATASET_DIR if they live elsewhere)")
+    splits, multilabel = parse_subgraph_file(sub_path)
+    order = ["train", "val", "test"]
+    if len(splits["val"][0]) < len(splits["test"][0]):
+        order = ["train", "test", "val"]
+    rows = [r for k in order for r in splits[k][0]]
+    labels = [l for k in order for l in splits[k][1]]
+    mask = torch.cat([torch.full((len(splits[k][0]),), i, dtype=torch.int64) for i, k in enumerate(order)])
+    if multilabel:
+        width = max(max(l) for l in labels) + 1
+        y = torch.zeros(len(labels), width)
+        for i, l in enumerate(labels):
+            y[i, torch.as_tensor(l, dtype=torch.int64)] = 1
+    else:
+        y = torch.tensor([l[0] for l in labels], dtype=torch.float)
+    pos = _pad_rows(rows)
+    raw = np.loadtxt(edge_path, dtype=np.int64, ndmin=2)[:, :2]
+    n = int(max(int(pos.max()), int(raw.max()))) + 1
+    # the reference reads the list into an undirected networkx Graph (:220), which keeps one copy of every
+    # unordered pair however often / in whichever direction the file lists it
+    und = np.unique(np.minimum(raw[:, 0], raw[:, 1]) * n + np.maximum(raw[:, 0], raw[:, 1]))
+    edge = torch.from_numpy(np.stack((und // n, und % n)))
+    return BaseGraph(torch.empty((n, 1, 0)), edge, torch.ones(edge.shape[1]), pos, y, mask)
+
+
+def pretrained_embedding(name: str, dim: int, n: int, seed: int = 0) -> torch.Tensor:
+    """./Emb/<dataset>_<dim>.pt (GLASSTest.py:153-157) when the file exists, else the seeded stand-in."""
+    path = os.path.join(os.environ.get("GLASS_EMB_DIR", "./Emb"), f"{name}_{dim}.pt")
+    if os.path.exists(path):
+        emb = torch.load(path, map_location="cpu").detach().to(torch.float32)
+        if emb.shape != (n, dim):
+            raise RuntimeError(f"{path}: expected shape {(n, dim)}, found {tuple(emb.shape)}")
+        return emb
+    return synthetic_embedding(n, dim, seed)

@@ -1,6 +1,7 @@
 """Label-batch data parallelism: the base graph, its CSR and the parameters are
 replicated on every GPU; rank r processes label batches r, r+P, ... of a permutation shared by all
-ranks; gradients are averaged with ONE all-reduce per step over a single flat fp32 buffer.
+ranks; gradients are averaged once per step (graphed.GradAverager: the table gradient in place, the small
+tensors through one flat buffer).
 
 The reference has no distributed code at all -- this is new capability, and because
 max-zero-one labels are per batch (impl/utils.py:40-44) P ranks = P independent batches per step
@@ -9,7 +10,7 @@ Backend: NCCL over NVLink on GPUs; gloo for the CPU tests of the host logic.
 """
 from __future__ import annotations
 
-from typing import Iterable, List
+from typing import List
 
 import torch
 import torch.distributed as dist
@@ -64,46 +65,3 @@ def sharded_test(model, dataloader, metrics, loss_fn, group=None):
         offs[r] += n
     pred = torch.cat(parts, dim=0)
     return metrics(pred.cpu().numpy(), y.cpu().numpy()), loss_fn(pred, y)
-
-
-class FlatGradAllReduce:
-    """Gives every parameter a .grad that is a view into one flat buffer and averages that buffer
-    across ranks with a single all-reduce (0.2 MB for --use_one models, 14.8 MB at the em_user shape
-    with a trainable N x 64 table)."""
-
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
-        self.params = [p for p in params if p.requires_grad]
-        self.group = group
-        total = sum(p.numel() for p in self.params)
-        ref = self.params[0]
-        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
-    @property
-    def world(self) -> int:
-        return dist.get_world_size(self.group) if dist.is_initialized() else 1
-
-    def zero(self) -> None:
-        """Replaces optimizer.zero_grad(): one memset instead of one per parameter; keeps the views."""
-        self.flat.zero_()
-
-    def check_views(self) -> None:
-        base = self.flat.data_ptr()
-        off = 0
-        for p in self.params:
-            if p.grad is None or p.grad.data_ptr() != base + off * self.flat.element_size():
-                raise RuntimeError("a parameter's .grad no longer aliases the flat buffer "
-                                   "(use FlatGradAllReduce.zero() instead of zero_grad(set_to_none=True))")
-            off += p.numel()
-
-    def allreduce_mean(self, async_op: bool = False):
-        if self.world == 1:
-            return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
-        if async_op:
-            return work
-        self.flat.div_(self.world)
-        return None

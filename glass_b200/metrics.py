@@ -13,9 +13,13 @@ def _micro_f1(y_true: np.ndarray, y_pred: np.ndarray) -> float:
 
 
 def binaryf1(pred, label):
-    """impl/metrics.py:5-12: threshold logits at 0, micro-F1 (multi-label capable)."""
-    pred_i = (pred > 0).astype(np.int64)
-    label_i = label.reshape(pred.shape[0], -1).astype(np.int64)
+    """impl/metrics.py:5-12: threshold logits at 0, then sklearn `f1_score(label[n, -1], pred, average="micro")`.
+    sklearn treats a single-column target as a BINARY problem and micro-averages over both classes, which is
+    the accuracy; only a real multi-label indicator matrix (more than one column) gets the tp/fp/fn formula."""
+    pred_i = (np.asarray(pred) > 0).astype(np.int64)
+    label_i = np.asarray(label).reshape(pred_i.shape[0], -1).astype(np.int64)
+    if label_i.shape[1] == 1:
+        return float(np.mean(label_i.reshape(-1) == pred_i.reshape(-1)))
     return _micro_f1(label_i, pred_i.reshape(label_i.shape))
 
 

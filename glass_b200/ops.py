@@ -402,6 +402,8 @@ class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj: CSRAdj):
         x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
+        if x.shape[0] != adj.n:
+            raise RuntimeError(f"spmm: x has {x.shape[0]} rows but the adjacency is {adj.n} x {adj.n}")
         y = torch.empty((adj.n, x.shape[1]), dtype=torch.float32, device=x.device)
         _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, x, y)
         ctx.adj = adj
@@ -610,11 +612,32 @@ def graph_norm_cat(xs: Sequence[torch.Tensor], weight, bias, mean_scale, eps: fl
     return _GraphNormCat.apply(weight, bias, mean_scale, eps, *xs)
 
 
+_ids_checked = {}
+
+
+def _validate_ids(ids: torch.Tensor, rows: int, what: str) -> None:
+    """torch's nn.Embedding / index ops raise on an out-of-range index; the kernels cannot (no host sync), so
+    the range is checked on the host once per index tensor (one sync, cached by address and version -- the
+    node-id tensor of a dataset never changes) and skipped while a CUDA graph is being captured."""
+    if ids.numel() == 0 or torch.cuda.is_current_stream_capturing():
+        return
+    key = (ids.data_ptr(), ids._version, ids.numel(), str(ids.device), rows)
+    if key in _ids_checked:
+        return
+    lo, hi = int(ids.min()), int(ids.max())
+    if lo < 0 or hi >= rows:
+        raise IndexError(f"{what}: index out of range [0, {rows}) (min {lo}, max {hi})")
+    if len(_ids_checked) > 64:
+        _ids_checked.clear()
+    _ids_checked[key] = True
+
+
 class _Embedding(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, table):
         ids = _req(ids, torch.int64, "ids").reshape(-1)
         table = _req(table, torch.float32, "table", 2)
+        _validate_ids(ids, table.shape[0], "embedding")
         out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
         _ops.embedding_fwd_(table, ids, out)
         ctx.save_for_backward(ids)

@@ -37,8 +37,18 @@ class FusedAdam:
                 cb.append(b)
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
         self.chunk_begin = torch.tensor(cb, dtype=torch.int64, device=dev)
-        self._table_host = torch.zeros((len(self.params), 5), dtype=torch.int64).pin_memory()
-        self._table_dev = torch.zeros((len(self.params), 5), dtype=torch.int64, device=dev)
+        # Pointer table {p, g, m, v, n} per tensor.  Eager steps: a ring of pinned staging buffers, each guarded by
+        # an event (the CPU may run ahead of the GPU; a queued H2D copy must never see a rewritten buffer) and an
+        # upload only when an address changed.  Captured steps: a device table and a pinned buffer of their OWN
+        # (allocated here, never rewritten after the capture), so later eager steps cannot corrupt a graph.
+        shape = (len(self.params), 5)
+        self._stage = [(torch.zeros(shape, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+        self._stage_i = 0
+        self._last_rows = None
+        self._table_dev = torch.zeros(shape, dtype=torch.int64, device=dev)
+        self._capture_pool = [(torch.zeros(shape, dtype=torch.int64).pin_memory(),
+                               torch.zeros(shape, dtype=torch.int64, device=dev)) for _ in range(4)]
+        self._captured = []
         self.device = dev
 
     def zero_grad(self, set_to_none: bool = True):
@@ -60,9 +70,7 @@ class FusedAdam:
     def step(self):
         """Parameters without a gradient this step are skipped (like torch; the step count used for the bias
         correction is global here, per parameter in torch -- identical as long as every parameter receives a
-        gradient every step, which is the case for the GLASS model).  The pointer table is rebuilt on
-        every eager call; inside a CUDA-graph capture the (static) addresses are baked into the graph through a
-        pinned staging copy."""
+        gradient every step, which is the case for the GLASS model)."""
         rows = []
         for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq):
             g = p.grad
@@ -72,11 +80,26 @@ class FusedAdam:
             if not g.is_contiguous() or g.dtype != torch.float32:
                 raise RuntimeError("FusedAdam needs contiguous fp32 gradients")
             rows.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()))
-        self._table_host.copy_(torch.tensor(rows, dtype=torch.int64))
-        self._table_dev.copy_(self._table_host, non_blocking=True)
+        if torch.cuda.is_current_stream_capturing():
+            if not self._capture_pool:
+                raise RuntimeError("FusedAdam: more than 4 captures of one optimizer")
+            host, table = self._capture_pool.pop()
+            host.copy_(torch.tensor(rows, dtype=torch.int64))
+            table.copy_(host, non_blocking=True)       # memcpy node: replays re-read `host`, which is never rewritten
+            self._captured.append((host, table))
+        else:
+            table = self._table_dev
+            if rows != self._last_rows:
+                host, ev = self._stage[self._stage_i]
+                ev.synchronize()                        # the copy that last used this buffer has completed
+                host.copy_(torch.tensor(rows, dtype=torch.int64))
+                table.copy_(host, non_blocking=True)
+                ev.record()
+                self._stage_i = (self._stage_i + 1) % len(self._stage)
+                self._last_rows = rows
         lib = _lib.load()
         b1, b2 = self.betas
-        check(lib.glass_adam_step(C.c_void_p(self._table_dev.data_ptr()), C.c_void_p(self.chunk_tensor.data_ptr()),
+        check(lib.glass_adam_step(C.c_void_p(table.data_ptr()), C.c_void_p(self.chunk_tensor.data_ptr()),
                                   C.c_void_p(self.chunk_begin.data_ptr()), self.chunk_tensor.numel(),
                                   C.c_void_p(self.lr.data_ptr()), C.c_void_p(self.state.data_ptr()), b1, b2, self.eps,
                                   self.weight_decay, C.c_void_p(torch.cuda.current_stream().cuda_stream)),

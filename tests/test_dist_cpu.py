@@ -13,27 +13,31 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from glass_b200.dist import FlatGradAllReduce, shard_batches, shared_permutation
+    from glass_b200.dist import shard_batches, shared_permutation
+    from glass_b200.graphed import GradAverager
     torch.manual_seed(0)
+    # one "big" tensor (reduced in place, like the N x H embedding table) and several small ones (flat buffer)
     model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
-    flat = FlatGradAllReduce(model.parameters())
+    GradAverager.BIG = 10
+    params = list(model.parameters())
+    avg = GradAverager(params)
+    assert len(avg.big) == 1 and len(avg.small) == 3
     perm = shared_permutation(20, seed=7, epoch=1)
     mine = shard_batches(10, rank, world)
     data = torch.arange(80, dtype=torch.float32).reshape(20, 4)
-    losses = []
     for b in mine[:2]:
         idx = perm[b * 2:(b + 1) * 2]
-        flat.zero()
+        for p in params:
+            p.grad = None
         loss = model(data[idx]).sum()
         loss.backward()
-        flat.check_views()
-        local = flat.flat.clone()
-        flat.allreduce_mean()
+        local = torch.cat([p.grad.flatten() for p in params])
+        avg()                                   # the product path's averaging (graphed.GraphedTrainStep calls this)
         gathered = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
-        assert torch.allclose(flat.flat, sum(gathered) / world)
-        losses.append(float(loss))
-    out[rank] = (perm.tolist(), mine, flat.flat.tolist())
+        now = torch.cat([p.grad.flatten() for p in params])
+        assert torch.allclose(now, sum(gathered) / world)
+    out[rank] = (perm.tolist(), mine, now.tolist())
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,0 +1,247 @@
+"""GPU: oracle parity at the sizes bench.py measures (BASELINE.json configs[1..3]).
+
+Round-1 parity ran at n <= 4,096 rows; the tcgen05 pair GEMM only reaches >= 3 tiles per CTA (the TMEM
+double-buffer phase logic) when n > 2 * 148 * 128 = 37,888, i.e. only on the em_user shape.  These tests run
+the CPU oracle (oracle/glass_oracle.py, ~1-4 s per step at these sizes) and the CUDA path on the SAME full
+graphs: eval forward (embeddings, pooled vectors, logits) and one train step with injected dropout masks
+(loss and every parameter gradient), 1e-4 bar (reference: impl/models.py:153-174, 240-272, 352-355)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import glass_oracle as O
+from tests.helpers import keep_masks_for, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    from glass_b200 import build
+    build.build()
+    torch.cuda.set_device(0)
+
+
+_WORKLOADS = {}
+
+
+def _workload(name, emb):
+    """Graph + hyper-parameters of a bench.py workload, the product model and the oracle's view of it."""
+    key = (name, emb)
+    if key in _WORKLOADS:
+        return _WORKLOADS[key]
+    from glass_b200 import datasets, run
+    torch.manual_seed(0)
+    g = datasets.load_dataset(name)
+    p = run.load_params(name)
+    _, out_dim, _, y = run.task_of(g.y)
+    g.y = y
+    n = g.num_nodes
+    if emb == "one":
+        g.setOneFeature()
+        table, max_deg = None, 1
+    else:
+        g.setNodeIdFeature()
+        table, max_deg = datasets.synthetic_embedding(n, p["hidden_dim"], 0), n - 1
+    torch.manual_seed(1)
+    model = run.build_model(p["hidden_dim"], p["conv_layer"], p["dropout"], 1, p["pool"], p["z_ratio"], p["aggr"],
+                            max_deg, out_dim, pretrained=table)
+    # non-trivial norm parameters (the initial ones / zeros would hide mistakes in their gradients)
+    gen = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for k, v in model.named_parameters():
+            if k.endswith("gn.weight") or ".gns." in k and k.endswith("weight"):
+                v.copy_(1.0 + 0.2 * torch.randn(v.shape, generator=gen))
+            elif k.endswith("mean_scale"):
+                v.copy_(1.0 + 0.1 * torch.randn(v.shape, generator=gen))
+            elif "gn" in k and k.endswith("bias"):
+                v.copy_(0.1 * torch.randn(v.shape, generator=gen))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cfg = O.GlassConfig(hidden_dim=p["hidden_dim"], conv_layer=p["conv_layer"], aggr=p["aggr"], z_ratio=p["z_ratio"],
+                        dropout=p["dropout"], pool=p["pool"], jk=True, activation="elu", out_dim=out_dim)
+    bs = p["batch_size"]
+    pos, yb = g.pos[:bs].contiguous(), g.y[:bs].contiguous()
+    adj = O.build_adj(g.edge_index, g.edge_attr, n, p["aggr"])
+    w = dict(g=g, p=p, model=model.to(DEV), sd=sd, cfg=cfg, pos=pos, y=yb, adj=adj, n=n, out_dim=out_dim,
+             binary=(out_dim == 1 and g.y.dtype == torch.float32), emb=emb)
+    _WORKLOADS[key] = w
+    return w
+
+
+def _tol(k, w):
+    # --use_one: emb_gn sees zero variance; its output and the gradients through it are amplified rounding
+    # noise in ANY implementation (DESIGN.md "Parity bars"), compared loosely
+    if w["emb"] == "one" and ("input_emb" in k or "emb_gn" in k):
+        return 5e-2
+    return TOL
+
+
+CASES = [("em_user_shaped", "nodeid"), ("em_user_shaped_powerlaw", "nodeid"), ("ppi_bp_shaped", "nodeid"),
+         ("cut_ratio", "nodeid"), ("component", "nodeid"), ("density", "nodeid"), ("coreness", "nodeid")]
+
+
+@pytest.mark.parametrize("name,emb", CASES)
+def test_full_size_eval_forward_matches_oracle(name, emb):
+    from glass_b200 import utils
+    w = _workload(name, emb)
+    g, m = w["g"], w["model"].eval()
+    z_ref = O.max_zero_one(w["n"], w["pos"])
+    with torch.no_grad():
+        ref_logits, ref_pooled, ref_emb = O.glass_forward(w["sd"], g.x, w["adj"], w["pos"], z_ref, w["cfg"])
+        x, ei, ew, pos = g.x.to(DEV), g.edge_index.to(DEV), g.edge_attr.to(DEV), w["pos"].to(DEV)
+        z = utils.MaxZOZ(x, pos)
+        assert torch.equal(z.cpu(), z_ref)                                   # label masks: bit-exact
+        emb_t = m.NodeEmb(x, ei, ew, z)
+        pooled = m.Pool(emb_t, pos, m.pools[0])
+        logits = m(x, ei, ew, pos, z)
+    assert rel_err(emb_t.cpu(), ref_emb) < TOL
+    assert rel_err(pooled.cpu(), ref_pooled) < TOL
+    assert rel_err(logits.cpu(), ref_logits) < TOL
+
+
+@pytest.mark.parametrize("name,emb", CASES)
+def test_full_size_train_step_matches_oracle(name, emb):
+    """Train-mode pass with the SAME explicit dropout keep-masks in both implementations: loss and every
+    parameter gradient (incl. the dense N x H embedding-table gradient)."""
+    from glass_b200 import ops, utils
+    w = _workload(name, emb)
+    g, m, cfg = w["g"], w["model"].train(), w["cfg"]
+    p = max(cfg.dropout, 0.3)                     # shipped configs with p = 0 still exercise the mask path
+    cfg_t = O.GlassConfig(**{**cfg.__dict__, "dropout": p})
+    raw = dict(H=cfg.hidden_dim, L=cfg.conv_layer)
+    keeps = keep_masks_for(raw, w["n"], p, seed=7)
+    sd = {k: v.clone().requires_grad_(True) for k, v in w["sd"].items()}
+    z_ref = O.max_zero_one(w["n"], w["pos"])
+    ref_logits, _, _ = O.glass_forward(sd, g.x, w["adj"], w["pos"], z_ref, cfg_t, training=True, keeps=keeps)
+    loss_fn = O.loss_fn_for(w["binary"])
+    ref_loss = loss_fn(ref_logits, w["y"])
+    ref_loss.backward()
+    # product model with the same dropout probability
+    old = {}
+    for mod in m.modules():
+        if hasattr(mod, "dropout") and not isinstance(mod, torch.nn.Dropout):
+            old[mod] = mod.dropout
+            mod.dropout = p
+    try:
+        x, ei, ew, pos = g.x.to(DEV), g.edge_index.to(DEV), g.edge_attr.to(DEV), w["pos"].to(DEV)
+        m.zero_grad(set_to_none=True)
+        with ops.inject_keep_masks([k.to(DEV) for k in keeps]):
+            logits = m(x, ei, ew, pos, utils.MaxZOZ(x, pos))
+        loss = loss_fn(logits, w["y"].to(DEV))
+        loss.backward()
+    finally:
+        for mod, v in old.items():
+            mod.dropout = v
+    assert rel_err(logits.detach().cpu(), ref_logits.detach()) < TOL
+    assert abs(float(loss) - float(ref_loss)) < TOL * max(1.0, abs(float(ref_loss)))
+    for k, prm in m.named_parameters():
+        assert prm.grad is not None, k
+        assert rel_err(prm.grad.cpu(), sd[k].grad) < _tol(k, w), k
+
+
+@pytest.mark.parametrize("name", ["cut_ratio", "component"])
+def test_full_size_use_one_configs_match_oracle_loosely(name):
+    """The reference's own README configuration (--use_one) on the shipped graphs at real size.  Degenerate
+    emb_gn input (zero variance): the exact output is `bias`; fp32 residues differ between any two
+    implementations and GraphNorm amplifies them by 1/sqrt(eps), so the bar is 2e-2."""
+    from glass_b200 import utils
+    w = _workload(name, "one")
+    g, m = w["g"], w["model"].eval()
+    z_ref = O.max_zero_one(w["n"], w["pos"])
+    with torch.no_grad():
+        ref_logits, _, _ = O.glass_forward(w["sd"], g.x, w["adj"], w["pos"], z_ref, w["cfg"])
+        x, ei, ew, pos = g.x.to(DEV), g.edge_index.to(DEV), g.edge_attr.to(DEV), w["pos"].to(DEV)
+        logits = m(x, ei, ew, pos, utils.MaxZOZ(x, pos))
+    assert rel_err(logits.cpu(), ref_logits) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------ kernels at n = 57,333
+def _pair_ref(a, w0, b0, w1, b1, mask, z, act):
+    f = {0: (lambda t: t), 1: torch.relu, 2: torch.nn.functional.elu}[act]
+    p0 = f(torch.nn.functional.linear(a, w0, b0))
+    p1 = f(torch.nn.functional.linear(a, w1, b1))
+    return torch.where(mask.bool().view(-1, 1), z * p1 + (1 - z) * p0, z * p0 + (1 - z) * p1)   # models.py:161
+
+
+@pytest.mark.parametrize("n,k1,k2,h,act,z", [(57333, 64, 0, 64, 2, 0.75), (57333, 64, 64, 64, 0, 0.75),
+                                            (57333, 64, 0, 64, 0, 0.8), (57333, 64, 64, 64, 2, 0.9),
+                                            (40000, 128, 0, 128, 2, 0.6), (17080, 64, 64, 64, 0, 0.95)])
+def test_pair_linear_mix_full_size_vs_fp64(n, k1, k2, h, act, z):
+    """>= 3 row tiles per CTA on 148 SMs: the TMEM double-buffer / ring phase arithmetic of k_pair_tc, the
+    dX kernel and the split-N dW kernel at the benchmarked row count, against fp64."""
+    from glass_b200 import _lib, ops
+    g = torch.Generator().manual_seed(n + h + k2)
+    a1 = torch.randn(n, k1, generator=g)
+    a2 = torch.randn(n, k2, generator=g) if k2 else None
+    k = k1 + k2
+    w0, w1 = torch.randn(h, k, generator=g) / k ** 0.5, torch.randn(h, k, generator=g) / k ** 0.5
+    b0, b1 = torch.randn(h, generator=g), torch.randn(h, generator=g)
+    mask = (torch.rand(n, generator=g) > 0.9).to(torch.uint8)
+    gout = torch.randn(n, h, generator=g)
+    cpu = [t.double().requires_grad_(True) if t is not None else None for t in (a1, a2, w0, b0, w1, b1)]
+    a_cat = cpu[0] if a2 is None else torch.cat((cpu[0], cpu[1]), dim=-1)
+    ref = _pair_ref(a_cat, cpu[2], cpu[3], cpu[4], cpu[5], mask, z, act)
+    ref.backward(gout.double())
+    dev = [t.to(DEV).requires_grad_(True) if t is not None else None for t in (a1, a2, w0, b0, w1, b1)]
+    out = ops.pair_linear_mix(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], mask.to(DEV), z, act, _lib.GEMM_AUTO)
+    assert rel_err(out.cpu(), ref) < 2e-5
+    # row-wise check as well: a wrong tile would be invisible in a max-norm dominated by other rows
+    err_rows = ((out.cpu().double() - ref).abs().amax(dim=1) / ref.abs().amax(dim=1).clamp(min=1e-3))
+    assert float(err_rows.max()) < 1e-4
+    out.backward(gout.to(DEV))
+    for name, c, d in zip(("a1", "a2", "w0", "b0", "w1", "b1"), cpu, dev):
+        if c is not None:
+            assert rel_err(d.grad.cpu(), c.grad) < 5e-5, name
+
+
+@pytest.mark.parametrize("n,c,act,p", [(57333, 64, 0, 0.5), (57333, 64, 2, 0.5), (17080, 128, 0, 0.0)])
+def test_graph_norm_full_size(n, c, act, p):
+    from glass_b200 import ops
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, c, generator=g) * 3 + torch.randn(1, c, generator=g) * 5
+    w, b, a = (torch.randn(c, generator=g) for _ in range(3))
+    a = a * 0.3 + 1.0
+    keep = (torch.rand(n, c, generator=g) >= p).to(torch.uint8) if p > 0 else None
+    gout = torch.randn(n, c, generator=g)
+    cpu = [t.double().requires_grad_(True) for t in (x, w, b, a)]
+    f = {0: (lambda t: t), 1: torch.relu, 2: torch.nn.functional.elu}[act]
+    ref = f(O.graph_norm(*cpu))
+    if keep is not None:
+        ref = ref * keep.double() / (1 - p)
+    ref.backward(gout.double())
+    dev = [t.to(DEV).requires_grad_(True) for t in (x, w, b, a)]
+    if keep is not None:
+        with ops.inject_keep_masks([keep.to(DEV)]):
+            out = ops.graph_norm(*dev, 1e-5, act, p, True)
+    else:
+        out = ops.graph_norm(*dev, 1e-5, act, p, True)
+    assert rel_err(out.cpu(), ref) < 2e-5
+    out.backward(gout.to(DEV))
+    for name, cc, d in zip(("x", "weight", "bias", "mean_scale"), cpu, dev):
+        assert rel_err(d.grad.cpu(), cc.grad) < TOL, name
+
+
+@pytest.mark.parametrize("name", ["em_user_shaped", "em_user_shaped_powerlaw"])
+def test_full_size_spmm_matches_oracle_sparse_mm(name):
+    """adj @ x and adj^T @ gy on the full graph against the reference's own op (sparse COO @ dense on the
+    CPU, impl/models.py:164) -- the round-1 test compared sampled rows only."""
+    from glass_b200 import ops
+    w = _workload(name, "nodeid")
+    g, n = w["g"], w["n"]
+    adj = ops.build_csr(g.edge_index.to(DEV), g.edge_attr.to(DEV), n, "gcn")
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(n, 64, generator=gen)
+    gy = torch.randn(n, 64, generator=gen)
+    ref_adj = w["adj"]
+    ref = ref_adj @ x
+    ref_t = ref_adj.t() @ gy
+    xd = x.to(DEV).requires_grad_(True)
+    y = ops.spmm(adj, xd)
+    y.backward(gy.to(DEV))
+    assert rel_err(y.detach().cpu(), ref) < 1e-5
+    assert rel_err(xd.grad.cpu(), ref_t) < 1e-5
+    # per-row bound (hub rows of the power-law graph go through the split-row plan)
+    rows = (y.detach().cpu() - ref).abs().amax(dim=1) / ref.abs().amax(dim=1).clamp(min=1e-3)
+    assert float(rows.max()) < 1e-4

@@ -423,9 +423,10 @@ def test_row_partitioned_spmm_single_device_emulation(world, overlap):
     adj = ops.build_csr(ei.to(DEV), ew.to(DEV), n, "mean")
     x = torch.randn(n, h, generator=torch.Generator().manual_seed(1)).to(DEV)
     gy = torch.randn(n, h, generator=torch.Generator().manual_seed(2)).to(DEV)
-    xf = x.clone().requires_grad_(True)
-    y_ref = ops.spmm(adj, xf)
-    y_ref.backward(gy)
+    # reference op on the CPU (sparse COO @ dense, impl/models.py:164) -- not the CUDA path against itself
+    xf = x.cpu().requires_grad_(True)
+    y_ref = O.build_adj(ei, ew, n, "mean") @ xf
+    y_ref.backward(gy.cpu())
     parts = [RowPartitionedAdj(adj, r, world, overlap=overlap) for r in range(world)]
     nnz = [p.nnz_local for p in parts]
     if overlap:
@@ -451,9 +452,9 @@ def test_row_partitioned_spmm_single_device_emulation(world, overlap):
 
         p.gather_override = fake_gather
         y = p.spmm(xs)
-        assert rel_err(y.detach().cpu(), y_ref[p.lo:p.hi].detach().cpu()) < 5e-6
+        assert rel_err(y.detach().cpu(), y_ref[p.lo:p.hi].detach()) < 1e-5
         y.backward(gy[p.lo:p.hi].contiguous())
-        assert rel_err(xs.grad.cpu(), xf.grad[p.lo:p.hi].cpu()) < 5e-6
+        assert rel_err(xs.grad.cpu(), xf.grad[p.lo:p.hi]) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------ optimizer

@@ -129,7 +129,7 @@ def test_loaders_follow_the_torch_dataloader_order():
     from torch.utils.data import DataLoader
     from glass_b200 import SubGDataset
     n = 23
-    ds = SubGDataset.GDataset(torch.zeros(5, 1), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0),
+    ds = SubGDataset.GDataset(torch.zeros(n * 4, 1), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0),
                               torch.arange(n * 4).reshape(n, 4), torch.arange(n))
     for shuffle, drop_last in ((True, True), (True, False), (False, False)):
         ref_loader = DataLoader(torch.arange(n), batch_size=5, shuffle=shuffle, drop_last=drop_last)
@@ -149,7 +149,7 @@ def test_loaders_follow_the_torch_dataloader_order():
             assert torch.equal(rp, ip) and torch.equal(ry, iy) and torch.equal(rp, ep) and torch.equal(ry, ey)
         assert torch.equal(after_ref, after_iter) and torch.equal(after_ref, after_epoch)   # same RNG consumption
     b = next(iter(SubGDataset.ZGDataloader(ds, 4, shuffle=False)))
-    assert len(b) == 6 and b[4].shape == (5, 1) and b[4].dtype == torch.int64 and loader.get_pos() is ds.pos
+    assert len(b) == 6 and b[4].shape == (n * 4, 1) and b[4].dtype == torch.int64 and loader.get_pos() is ds.pos
 
 
 def test_train_and_test_epoch_drivers_follow_the_reference_loop():
@@ -215,3 +215,93 @@ def test_pretraining_modules_state_dict_layout_matches_reference_golden():
     assert models.AddPool(trans_fn=nn.Identity()).padded_mode() is None
     one = models.EmbGConv(8, 16, 4, 1, max_deg=3)
     assert [tuple(c.trans_fn.weight.shape) for c in one.convs] == [(4, 8)] and len(one.gns) == 0
+
+
+def test_binaryf1_and_microf1_match_sklearn():
+    """impl/metrics.py:5-20 call sklearn f1_score(average="micro"): a single-column binary target is scored as
+    a binary problem over both classes (= accuracy), a wider indicator matrix as multi-label tp/fp/fn."""
+    from sklearn.metrics import f1_score
+    from glass_b200 import metrics
+    g = np.random.default_rng(0)
+    n = 200
+    logits = g.normal(size=(n, 1))
+    for label in (g.integers(0, 2, n).astype(np.float32), g.integers(0, 2, (n, 1)).astype(np.float32)):
+        ref = f1_score(label.reshape(n, -1), (logits > 0).astype(np.int64), average="micro")
+        assert abs(metrics.binaryf1(logits, label) - ref) < 1e-12
+    ml_logits, ml_label = g.normal(size=(n, 5)), g.integers(0, 2, (n, 5)).astype(np.float32)
+    ref = f1_score(ml_label, (ml_logits > 0).astype(np.int64), average="micro")
+    assert abs(metrics.binaryf1(ml_logits, ml_label) - ref) < 1e-12
+    mc_logits, mc_label = g.normal(size=(n, 6)), g.integers(0, 6, n)
+    ref = f1_score(mc_label, mc_logits.argmax(1), average="micro")
+    assert abs(metrics.microf1(mc_logits, mc_label) - ref) < 1e-12
+
+
+def test_gdataset_rejects_node_ids_outside_the_graph():
+    from glass_b200 import SubGDataset
+    with pytest.raises(IndexError):
+        SubGDataset.GDataset(torch.zeros(5, 1), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0),
+                             torch.tensor([[0, 7, -1]]), torch.zeros(1))
+
+
+def _write_fake_real_dataset(root, name, multilabel):
+    """A tiny dataset in the SubGNN text format the reference parses (datasets.py:131-222)."""
+    d = os.path.join(root, "dataset", name)
+    os.makedirs(d)
+    g = np.random.default_rng(3)
+    n = 40
+    edges = {(int(a), int(b)) for a, b in g.integers(0, n, (150, 2))}
+    with open(os.path.join(d, "edge_list.txt"), "w") as f:
+        for a, b in sorted(edges):
+            f.write(f"{a} {b}\n")
+        f.write("3 1\n1 3\n")                                       # both directions of one pair
+    names = ["alpha", "beta", "gamma"]
+    with open(os.path.join(d, "subgraphs.pth"), "w") as f:
+        for i in range(30):
+            nodes = "-".join(str(int(v)) for v in g.choice(n, size=int(g.integers(2, 7)), replace=False))
+            k = int(g.integers(1, 3)) if multilabel else 1
+            labs = "-".join(g.choice(names, size=k, replace=False))
+            split = ["train", "train", "train", "val", "test", "test"][i % 6]     # val smaller than test -> swapped
+            f.write(f"{nodes}\t{labs}\t{split}\n")
+    return d
+
+
+@pytest.mark.parametrize("multilabel", [False, True])
+def test_real_dataset_loader_parses_the_subgnn_format(tmp_path, monkeypatch, multilabel):
+    from glass_b200 import datasets
+    _write_fake_real_dataset(str(tmp_path), "ppi_bp", multilabel)
+    monkeypatch.setenv("GLASS_DATASET_DIR", str(tmp_path / "dataset"))
+    g = datasets.load_dataset("ppi_bp")
+    assert g.pos.shape[0] == 30 and g.mask.tolist().count(0) == 15
+    assert g.mask.tolist().count(1) == 10 and g.mask.tolist().count(2) == 5     # val/test swapped (val was smaller)
+    assert g.y.dtype == torch.float32 and (g.y.ndim == 2) == multilabel
+    ei = g.edge_index
+    key = ei[0] * g.num_nodes + ei[1]
+    assert torch.equal(key, torch.unique(key))                                   # sorted, duplicate free
+    assert torch.equal(torch.unique(ei[1] * g.num_nodes + ei[0]), key)           # symmetric
+    off = ei[0] != ei[1]
+    assert torch.all(g.edge_attr[off] == 1.0)
+    with pytest.raises(FileNotFoundError):
+        datasets.load_dataset("em_user")
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("multilabel", [False, True])
+def test_real_dataset_loader_equals_the_reference_loader(tmp_path, monkeypatch, multilabel):
+    import sys
+    from glass_b200 import datasets
+    _write_fake_real_dataset(str(tmp_path), "hpo_metab", multilabel)
+    monkeypatch.setenv("GLASS_DATASET_DIR", str(tmp_path / "dataset"))
+    mine = datasets.load_dataset("hpo_metab")
+    ref_root = os.environ.get("GLASS_REFERENCE", "/root/reference")
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "pyg_shim")
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(shim)
+    monkeypatch.syspath_prepend(ref_root)
+    for m in [k for k in sys.modules if k == "datasets" or k.startswith("torch_geometric")]:
+        monkeypatch.delitem(sys.modules, m)
+    import datasets as ref_datasets
+    ref = ref_datasets.load_dataset("hpo_metab")
+    assert torch.equal(mine.edge_index, ref.edge_index) and torch.equal(mine.edge_attr, ref.edge_attr)
+    assert torch.equal(mine.pos, ref.pos) and torch.equal(mine.y, ref.y)
+    assert torch.equal(mine.mask.to(ref.mask.dtype), ref.mask)
+    assert mine.x.shape == ref.x.shape
