@@ -27,24 +27,37 @@ PROTOTYPES = {
     "glass_csr_build_workspace_bytes": (_sz, [_i64, _i64]),
     "glass_csr_build": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                C.POINTER(C.c_int64), _vp, _sz, _vp]),
-    "glass_spmm_csr": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
+    "glass_spmm_stats_ld": (_i32, []),
+    "glass_tune": (_i32, [C.c_char_p, _i32]),
+    "glass_spmm_csr": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i32, C.POINTER(C.c_int), _vp]),
     "glass_spmm_plan_size": (_i32, [_vp, _i64, _i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64), _vp]),
     "glass_spmm_plan_build": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "glass_spmm_csr_planned": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i64,
-                                      _vp, _vp, _vp, _i64, _vp, _vp]),
+                                      _vp, _vp, _vp, _i64, _vp, _vp, _i32, C.POINTER(C.c_int), _vp]),
     "glass_pair_linear_mix_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
                                          _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "glass_pair_norm_operand_supported": (_i32, [_i32, _i32, _i32]),
+    "glass_pair_linear_mix_fwd_ex": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
+                                            _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "glass_pair_linear_mix_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "glass_pair_linear_mix_bwd_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _f32,
+                                            _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _sz,
+                                            _i32, _vp, _vp, _i32, _i32, _vp]),
     "glass_pair_linear_mix_bwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _f32,
                                          _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _sz,
                                          _i32, _vp]),
     "glass_graphnorm_workspace_bytes": (_sz, [_i64, _i32]),
+    "glass_dropout_bits_bytes": (_sz, [_i64, _i32]),
     "glass_graphnorm_launches": (_i32, [_i64, _i32]),
-    "glass_graphnorm_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _f32, _i32, _vp, _f32, _vp, _vp, _i64, _vp, _i64,
+    "glass_graphnorm_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _f32, _i32, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _i64,
                                    _i32, _vp, _sz, _vp]),
-    "glass_graphnorm_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _i64, _vp,
+    "glass_graphnorm_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _vp, _i64, _vp,
                                    _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
+    "glass_graphnorm_stats": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "glass_graphnorm_apply": (_i32, [_vp, _i64, _vp, _i32, _vp, _f32, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "glass_graphnorm_bwd_from_sums": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
+                                             _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
     "glass_embedding_fwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "glass_embedding_bwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "glass_segment_pool_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _i64, _vp]),
@@ -57,6 +70,13 @@ PROTOTYPES = {
     "glass_label_mask": (_i32, [_vp, _vp, _i64, _vp]),
     "glass_pad2batch": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
+
+
+
+class NormOperand(C.Structure):
+    """glass_norm_operand of include/glass_b200.h."""
+    _fields_ = [("stats", C.c_void_p), ("bits", C.c_void_p), ("drop_p", C.c_float), ("act", C.c_int)]
+
 
 _lib = None
 
@@ -75,7 +95,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.glass_abi_version() != 1:
+    if lib.glass_abi_version() != 2:
         raise RuntimeError("libglass_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -96,6 +96,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
@@ -129,6 +141,16 @@ __device__ __forceinline__ uint32_t swz(int row, int ch) { return (uint32_t)(row
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+// Row operand normalised while it is loaded: v = keep/(1-p) * act(scale*(x - am) + bias) with the per-column
+// constants of a GraphNorm statistics table (rows 0, 1, 4 of stats[6, k]) and packed keep bits -- the GraphNorm
+// "apply" + dropout of impl/models.py:165-166 / 249-251 never materialises its output.
+struct NormOp {
+    const float* stats;
+    const uint32_t* bits;
+    float pscale;
+    int act;
+};
+
 struct TcParams {
     // forward: a1/a2 are the row operand; backward: dout/acts build dP
     const float* a1;
@@ -162,6 +184,9 @@ struct TcParams {
     int stages;
     uint32_t tmem_cols;
     int rows_per_tile;   // <= BM: rows a tile owns (chosen so that every CTA runs the same number of tiles)
+    NormOp n1, n2;       // forward: normalisation applied to a1 / a2 on load (stats == NULL: plain operand)
+    int acc1, acc2;      // backward: da1 / da2 += instead of =
+    int staged;          // epilogue goes through per-warp shared-memory tiles -> 64-byte row segments per store
     long long* dbg;      // optional timeline of CTA 0 (GLASS_B200_TC_TIMELINE): [0]=start [1]=setup done,
 };                       // [16+i] loader consumed K-block i, [80+i] MMA committed K-block i, [144+t] epilogue done tile t, [200]=end
 
@@ -169,7 +194,7 @@ __device__ __forceinline__ void stamp(long long* dbg, int idx) {
     if (dbg && blockIdx.x == 0) dbg[idx] = clock64();
 }
 
-template <bool BWD>
+template <bool BWD, bool NORM>
 __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -186,12 +211,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     uint64_t* tfull = bars + 2 * P.stages;     // [2]        mma -> epilogue
     uint64_t* tempty = tfull + 2;              // [2]        epilogue -> mma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [2H]: b0 | b1 (forward only), 16-byte aligned
+    float* s_norm = reinterpret_cast<float*>(tmem_slot + 4);   // NORM: [3][K] scale | am | bias, 16-byte aligned
+    float* s_stage = s_norm + (NORM ? 3 * K : 0);              // staged epilogue: [8 warps][arrays][32 rows][16 floats]
 
     if (threadIdx.x == 0) stamp(P.dbg, 0);
     // ---- one-time setup ------------------------------------------------------------------
-    if (!BWD)
-        for (int c = threadIdx.x; c < 2 * H; c += kThreads) s_bias[c] = c < H ? P.b0[c] : P.b1[c - H];
+    if (NORM) {
+        for (int k = threadIdx.x; k < K; k += kThreads) {
+            const bool first = k < P.k1;
+            const NormOp& op = first ? P.n1 : P.n2;
+            const int kk = first ? P.k1 : P.k2, c = first ? k : k - P.k1;
+            float sc = 1.f, am = 0.f, bs = 0.f;      // identity: fmaf(1, x - 0, 0) == x
+            if (op.stats) {
+                sc = op.stats[0 * kk + c];
+                am = op.stats[1 * kk + c];
+                bs = op.stats[4 * kk + c];
+            }
+            s_norm[k] = sc;
+            s_norm[K + k] = am;
+            s_norm[2 * K + k] = bs;
+        }
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(smem_u32(full + s), kLoadThreads);
@@ -254,6 +294,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             const int64_t row = tile * RT + quad * 32 + lane;
             const bool row_ok = row < P.n && quad * 32 + lane < RT;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N);
+            // Staged epilogue (widths that are multiples of 32): a lane owns a ROW in TMEM, so direct stores put 32
+            // different rows in every store instruction (16-byte pieces, one memory request each -- measured
+            // 10 K cycles per tile, the bottleneck of these kernels).  Instead each warp passes its 32 x 16 block
+            // through a private, XOR-swizzled shared-memory tile (conflict-free both ways) and writes 64-byte
+            // row segments: 8 rows per store instruction.
+            const int arrays = (!BWD && P.acts) ? 3 : 1;
+            float* st = s_stage + warp * (arrays * 512);
+            const int wr_sw = (lane >> 1) & 3;                          // write side: row == lane
+            bool released = false;
             if (!BWD) {
                 float c0 = 0.f, c1 = 0.f;
                 if (row_ok) {
@@ -261,14 +310,61 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     c1 = lab ? P.z : 1.f - P.z;
                     c0 = lab ? 1.f - P.z : P.z;
                 }
+                if (P.staged) {
+                    const int c_lo = half * (H >> 1), c_hi = c_lo + (H >> 1);
+                    for (int cb = c_lo; cb < c_hi; cb += 16) {
+                        float p0[16], p1[16];
+                        tmem_ld16(t_row + (uint32_t)cb, p0);
+                        tmem_ld16(t_row + (uint32_t)(H + cb), p1);
+                        tmem_ld_wait();
+                        if (cb + 16 >= c_hi) {          // last TMEM read of this tile: hand the accumulator back now
+                            tc_fence_before();
+                            mbar_arrive(smem_u32(tempty + acc));
+                            released = true;
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) {
+                            const float4 ba = ldg_f4(P.b0 + cb + 4 * ch), bb = ldg_f4(P.b1 + cb + 4 * ch);   // 512 B, L1 resident
+                            float4 q0, q1, o4;
+                            q0.x = act_fwd(p0[4 * ch] + ba.x, P.act), q0.y = act_fwd(p0[4 * ch + 1] + ba.y, P.act);
+                            q0.z = act_fwd(p0[4 * ch + 2] + ba.z, P.act), q0.w = act_fwd(p0[4 * ch + 3] + ba.w, P.act);
+                            q1.x = act_fwd(p1[4 * ch] + bb.x, P.act), q1.y = act_fwd(p1[4 * ch + 1] + bb.y, P.act);
+                            q1.z = act_fwd(p1[4 * ch + 2] + bb.z, P.act), q1.w = act_fwd(p1[4 * ch + 3] + bb.w, P.act);
+                            o4.x = __fadd_rn(__fmul_rn(c1, q1.x), __fmul_rn(c0, q0.x));
+                            o4.y = __fadd_rn(__fmul_rn(c1, q1.y), __fmul_rn(c0, q0.y));
+                            o4.z = __fadd_rn(__fmul_rn(c1, q1.z), __fmul_rn(c0, q0.z));
+                            o4.w = __fadd_rn(__fmul_rn(c1, q1.w), __fmul_rn(c0, q0.w));
+                            const int o = lane * 16 + ((ch ^ wr_sw) << 2);
+                            *reinterpret_cast<float4*>(st + o) = o4;
+                            if (arrays == 3) {
+                                *reinterpret_cast<float4*>(st + 512 + o) = q0;
+                                *reinterpret_cast<float4*>(st + 1024 + o) = q1;
+                            }
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = i * 8 + (lane >> 2), ch = lane & 3;
+                            const int o = r * 16 + ((ch ^ ((r >> 1) & 3)) << 2);
+                            const int64_t grow = tile * RT + quad * 32 + r;
+                            if (grow < P.n && quad * 32 + r < RT) {
+                                *reinterpret_cast<float4*>(P.out + grow * P.ldo + cb + 4 * ch) = *reinterpret_cast<const float4*>(st + o);
+                                if (arrays == 3) {
+                                    float* pa = P.acts + grow * (2 * (int64_t)H) + cb + 4 * ch;
+                                    *reinterpret_cast<float4*>(pa) = *reinterpret_cast<const float4*>(st + 512 + o);
+                                    *reinterpret_cast<float4*>(pa + H) = *reinterpret_cast<const float4*>(st + 1024 + o);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                } else {
                 for (int c = half * 8; c < H; c += 16) {
                     float p0[8], p1[8];
                     tmem_ld8(t_row + (uint32_t)c, p0);
                     tmem_ld8(t_row + (uint32_t)(H + c), p1);
-                    const float4 ba0 = *reinterpret_cast<const float4*>(s_bias + c);
-                    const float4 ba1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
-                    const float4 bb0 = *reinterpret_cast<const float4*>(s_bias + H + c);
-                    const float4 bb1 = *reinterpret_cast<const float4*>(s_bias + H + c + 4);
+                    const float4 ba0 = ldg_f4(P.b0 + c), ba1 = ldg_f4(P.b0 + c + 4);   // biases: 512 B, L1 resident
+                    const float4 bb0 = ldg_f4(P.b1 + c), bb1 = ldg_f4(P.b1 + c + 4);
                     const float bA[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
                     const float bB[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
                     tmem_ld_wait();
@@ -293,6 +389,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         }
                     }
                 }
+                }
+            } else if (P.staged) {
+                const int c_lo = half * (N >> 1), c_hi = c_lo + (N >> 1);
+                for (int cb = c_lo; cb < c_hi; cb += 16) {
+                    float d[16];
+                    tmem_ld16(t_row + (uint32_t)cb, d);
+                    tmem_ld_wait();
+                    if (cb + 16 >= c_hi) {
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(tempty + acc));
+                        released = true;
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        *reinterpret_cast<float4*>(st + lane * 16 + ((ch ^ wr_sw) << 2)) = make_float4(d[4 * ch], d[4 * ch + 1], d[4 * ch + 2], d[4 * ch + 3]);
+                    __syncwarp();
+                    const bool first = cb < P.k1;                        // k1 % 16 == 0: a block never straddles a1 | a2
+                    float* base = first ? P.da1 : P.da2;
+                    const int64_t ldd = first ? P.ldda1 : P.ldda2;
+                    const int cc = first ? cb : cb - P.k1;
+                    const int accum = first ? P.acc1 : P.acc2;
+                    if (base) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = i * 8 + (lane >> 2), ch = lane & 3;
+                            const int64_t grow = tile * RT + quad * 32 + r;
+                            if (grow < P.n && quad * 32 + r < RT) {
+                                float4 v = *reinterpret_cast<const float4*>(st + r * 16 + ((ch ^ ((r >> 1) & 3)) << 2));
+                                float4* dst = reinterpret_cast<float4*>(base + grow * ldd + cc + 4 * ch);
+                                if (accum) {     // the operand also fed another GEMM: add to its gradient
+                                    const float4 o = *dst;
+                                    v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+                                }
+                                *dst = v;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
             } else {
                 for (int c = half * 8; c < N; c += 16) {
                     float d[8];
@@ -306,14 +441,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                             dst = P.da2 + row * P.ldda2 + (c - P.k1);
                         }
                         if (dst) {
+                            if (c < P.k1 ? P.acc1 : P.acc2) {      // the operand also fed another GEMM: add to its gradient
+                                const float4 o0 = reinterpret_cast<const float4*>(dst)[0], o1 = reinterpret_cast<const float4*>(dst)[1];
+                                d[0] += o0.x, d[1] += o0.y, d[2] += o0.z, d[3] += o0.w;
+                                d[4] += o1.x, d[5] += o1.y, d[6] += o1.z, d[7] += o1.w;
+                            }
                             reinterpret_cast<float4*>(dst)[0] = make_float4(d[0], d[1], d[2], d[3]);
                             reinterpret_cast<float4*>(dst)[1] = make_float4(d[4], d[5], d[6], d[7]);
                         }
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(smem_u32(tempty + acc));
+            if (!released) {
+                tc_fence_before();
+                mbar_arrive(smem_u32(tempty + acc));
+            }
             if (threadIdx.x == 0 && it < 50) stamp(P.dbg, 144 + it);
         }
     } else if (warp == kEpiWarps) {
@@ -362,8 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
         struct Raw {
             float4 g[kCPT];
             float4 a[BWD ? kCPT : 1];
-            uint32_t lab[BWD ? kCPT : 1];   // raw label byte: turned into the mix coefficient only when consumed,
-        };                                    // so that issuing a stage never waits on a load
+            uint32_t lab[(BWD || NORM) ? kCPT : 1];   // BWD: raw label byte, NORM: raw keep-bit word; decoded only when
+        };                                              // consumed, so that issuing a stage never waits on a load
         Raw ring[D];
 
         auto issue = [&](int64_t seq, Raw& rw) {
@@ -380,9 +522,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     rw.a[i] = make_float4(1.f, 1.f, 1.f, 1.f);
                     rw.lab[i] = 2u;              // 2 = row / column out of range -> coefficient 0
                 }
+                if (NORM) rw.lab[i] = 0xffffffffu;
                 if (row < P.n && k < K) {
                     if (!BWD) {
                         rw.g[i] = (k < P.k1) ? ldg_f4(P.a1 + row * P.lda1 + k) : ldg_f4(P.a2 + row * P.lda2 + (k - P.k1));
+                        if (NORM) {     // keep bits of this chunk's 32-column word (operand widths are multiples of 32)
+                            const bool first = k < P.k1;
+                            const uint32_t* bits = first ? P.n1.bits : P.n2.bits;
+                            const int kk = first ? P.k1 : P.k2, c = first ? k : k - P.k1;
+                            if (bits) rw.lab[i] = __ldg(bits + row * (kk >> 5) + (c >> 5));
+                        }
                     } else {
                         // dP[row][k..k+3]: k indexes the 2H pre-activation columns (branch 0 | branch 1)
                         const int br = k >= H;
@@ -404,6 +553,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                 const int q = lt + i * kLoadThreads;
                 const uint32_t off = swz(q >> 3, q & 7);
                 float4 v = rw.g[i];
+                if (NORM) {
+                    const int k = kb_of_slot * KBF + (q & 7) * 4;
+                    const NormOp& op = k < P.k1 ? P.n1 : P.n2;
+                    if (op.stats && k < K) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_norm + k);
+                        const float4 am = *reinterpret_cast<const float4*>(s_norm + K + k);
+                        const float4 bs = *reinterpret_cast<const float4*>(s_norm + 2 * K + k);
+                        const uint32_t nib = rw.lab[i] >> ((q & 7) * 4);
+                        v.x = act_fwd(fmaf(sc.x, v.x - am.x, bs.x), op.act) * ((nib & 1u) ? op.pscale : 0.f);
+                        v.y = act_fwd(fmaf(sc.y, v.y - am.y, bs.y), op.act) * ((nib & 2u) ? op.pscale : 0.f);
+                        v.z = act_fwd(fmaf(sc.z, v.z - am.z, bs.z), op.act) * ((nib & 4u) ? op.pscale : 0.f);
+                        v.w = act_fwd(fmaf(sc.w, v.w - am.w, bs.w), op.act) * ((nib & 8u) ? op.pscale : 0.f);
+                    }
+                }
                 if (BWD) {
                     // chunk q & 7 of this K-block covers pre-activation columns of ONE branch (H % 4 == 0)
                     const int br = (kb_of_slot * KBF + (q & 7) * 4) >= H;
@@ -488,6 +651,7 @@ struct DwParams {
     int64_t rows_per_cta; // multiple of 32
     int stages;
     uint32_t tmem_cols;
+    NormOp n1, n2;        // a1 / a2 normalised on load, exactly as the forward loader does (stats == NULL: plain)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
@@ -505,6 +669,7 @@ __device__ __forceinline__ uint32_t swz_mn(int mn, int i) {
     return (uint32_t)((mn >> 5) * 4096 + (i >> 2) * 512 + (i & 3) * 128 + ((((c16 >> 1) ^ (i & 3)) << 5) | ((c16 & 1) << 4)));
 }
 
+template <bool NORM>
 __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -520,7 +685,24 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
     uint64_t* tfull = bars + 2 * P.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
     float* s_db = reinterpret_cast<float*>(tmem_slot + 4);   // [16][128]
+    float* s_norm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_db + 16 * 128) + 15) & ~uintptr_t(15));   // NORM: [3][K]
 
+    if (NORM) {
+        for (int k = threadIdx.x; k < K; k += kDwThreads) {
+            const bool first = k < P.k1;
+            const NormOp& op = first ? P.n1 : P.n2;
+            const int kk = first ? P.k1 : P.k2, c = first ? k : k - P.k1;
+            float sc = 1.f, am = 0.f, bs = 0.f;
+            if (op.stats) {
+                sc = op.stats[0 * kk + c];
+                am = op.stats[1 * kk + c];
+                bs = op.stats[4 * kk + c];
+            }
+            s_norm[k] = sc;
+            s_norm[K + k] = am;
+            s_norm[2 * K + k] = bs;
+        }
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(smem_u32(full + s), kDwLoadThreads);
@@ -579,6 +761,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
         struct Raw {
             float4 g[2], a[2], x[2];
             uint32_t lab[2];             // raw label byte (2 = row out of range); coefficient derived when consumed
+            uint32_t xw[NORM ? 2 : 1];   // NORM: keep-bit word of the x chunk (0 for rows out of range)
         };
         Raw ring[2];
         auto issue = [&](int64_t st, Raw& rw) {
@@ -597,10 +780,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
                 }
                 const int q = lt + t * kDwLoadThreads;
                 rw.x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NORM) rw.xw[t] = 0u;
                 if (q < kDwRows * kchunks) {
                     const int ib = q / kchunks, k = (q % kchunks) * 4;
                     const int64_t rowb = r0 + ib;
-                    if (rowb < m_hi) rw.x[t] = (k < P.k1) ? ldg_f4(P.a1 + rowb * P.lda1 + k) : ldg_f4(P.a2 + rowb * P.lda2 + (k - P.k1));
+                    if (rowb < m_hi) {
+                        rw.x[t] = (k < P.k1) ? ldg_f4(P.a1 + rowb * P.lda1 + k) : ldg_f4(P.a2 + rowb * P.lda2 + (k - P.k1));
+                        if (NORM) {
+                            const bool first = k < P.k1;
+                            const uint32_t* bits = first ? P.n1.bits : P.n2.bits;
+                            const int kk = first ? P.k1 : P.k2, c = first ? k : k - P.k1;
+                            rw.xw[t] = bits ? __ldg(bits + rowb * (kk >> 5) + (c >> 5)) : 0xffffffffu;
+                        }
+                    }
                 }
             }
         };
@@ -630,7 +822,21 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
                 const int q = lt + t * kDwLoadThreads;
                 if (q < kDwRows * kchunks) {
                     const int ib = q / kchunks, k = (q % kchunks) * 4;
-                    split_tf32(rw.x[t], hi, lo);
+                    float4 xv = rw.x[t];
+                    if (NORM) {
+                        const NormOp& op = k < P.k1 ? P.n1 : P.n2;
+                        if (op.stats) {
+                            const float4 sc = *reinterpret_cast<const float4*>(s_norm + k);
+                            const float4 am = *reinterpret_cast<const float4*>(s_norm + K + k);
+                            const float4 bs = *reinterpret_cast<const float4*>(s_norm + 2 * K + k);
+                            const uint32_t nib = rw.xw[t] >> ((k < P.k1 ? k : k - P.k1) & 31);
+                            xv.x = act_fwd(fmaf(sc.x, xv.x - am.x, bs.x), op.act) * ((nib & 1u) ? op.pscale : 0.f);
+                            xv.y = act_fwd(fmaf(sc.y, xv.y - am.y, bs.y), op.act) * ((nib & 2u) ? op.pscale : 0.f);
+                            xv.z = act_fwd(fmaf(sc.z, xv.z - am.z, bs.z), op.act) * ((nib & 4u) ? op.pscale : 0.f);
+                            xv.w = act_fwd(fmaf(sc.w, xv.w - am.w, bs.w), op.act) * ((nib & 8u) ? op.pscale : 0.f);
+                        }
+                    }
+                    split_tf32(xv, hi, lo);
                     const uint32_t offb = swz_mn(k, ib);
                     *reinterpret_cast<float4*>(base + 2 * a_bytes + offb) = hi;
                     *reinterpret_cast<float4*>(base + 2 * a_bytes + b_bytes + offb) = lo;
@@ -721,11 +927,13 @@ __global__ void __launch_bounds__(256) k_pair_dw_tc_reduce(const float* __restri
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // shared-memory plan; returns false when the shape does not fit
-bool plan(int kdim, int ndim, int* stages, size_t* bytes, uint32_t* tmem_cols) {
+bool plan(int kdim, int ndim, bool norm, int stage_arrays, int* stages, size_t* bytes, uint32_t* tmem_cols) {
     if (ndim < 16 || ndim > 256 || ndim % 16 || kdim < 8 || kdim % 8 || kdim > 512) return false;
     const int nkb = (kdim + KBF - 1) / KBF;
     const size_t b = (size_t)2 * nkb * ndim * 128;
-    const size_t fixed = b + 1024 /*alignment slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+    const size_t fixed = b + 1024 /*alignment slack*/ + 256 /*barriers, TMEM slot*/ +
+                         (norm ? (size_t)3 * kdim * sizeof(float) : 0) /*operand normalisation constants*/ +
+                         (size_t)stage_arrays * kEpiWarps * 512 * sizeof(float) /*staged epilogue tiles*/;
     if (fixed + 2 * (size_t)kStageBytes > (size_t)kMaxSmem) return false;
     int s = (int)(((size_t)kMaxSmem - fixed) / kStageBytes);
     if (s > 6) s = 6;
@@ -738,17 +946,23 @@ bool plan(int kdim, int ndim, int* stages, size_t* bytes, uint32_t* tmem_cols) {
     return true;
 }
 
-template <bool BWD>
+template <bool BWD, bool NORM>
 int launch(TcParams& P, cudaStream_t st) {
     size_t bytes = 0;
-    if (!plan(P.kdim, P.ndim, &P.stages, &bytes, &P.tmem_cols)) {
+    // staged epilogue: output width (forward: h, backward: k1 + k2 with the a1|a2 boundary on a 16-column block)
+    const int out_w = BWD ? P.ndim : P.h;
+    P.staged = (out_w % 32 == 0) && (!BWD || P.k1 % 16 == 0);
+    static const bool no_stage = getenv("GLASS_B200_TC_DIRECT_EPILOGUE") != nullptr;   // A/B switch for measurements
+    if (no_stage) P.staged = 0;
+    const int stage_arrays = P.staged ? ((!BWD && P.acts) ? 3 : 1) : 0;
+    if (!plan(P.kdim, P.ndim, NORM, stage_arrays, &P.stages, &bytes, &P.tmem_cols)) {
         set_error("pair_linear_mix (tcgen05): shape k=%d n=%d does not fit", P.kdim, P.ndim);
         return GLASS_ERR_UNSUPPORTED;
     }
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[BWD]) {
-        GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_done[BWD] = true;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_done = true;
     }
     // equal work per CTA: with 128-row tiles 57,333 rows are 448 tiles = 3.03 per SM, i.e. four rounds for a
     // few CTAs; shrink the rows a tile owns so that every CTA runs exactly ceil(tiles / #SMs) tiles
@@ -768,7 +982,7 @@ int launch(TcParams& P, cudaStream_t st) {
         GLASS_CUDA(cudaMemset(dbg, 0, 256 * sizeof(long long)));
         P.dbg = dbg;
     }
-    k_pair_tc<BWD><<<grid, kThreads, bytes, st>>>(P);
+    k_pair_tc<BWD, NORM><<<grid, kThreads, bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
     if (timeline) {   // debugging aid only: synchronises and prints CTA 0's event times in SM cycles
         long long h[256];
@@ -798,14 +1012,45 @@ bool pair_tc_supported(int k1, int k2, int h, int64_t lda1, int64_t lda2, const 
     int s;
     size_t b;
     uint32_t c;
-    return plan(k1 + k2, 2 * h, &s, &b, &c) && plan(2 * h, k1 + k2, &s, &b, &c);
+    const int fwd_arrays = (h % 32 == 0) ? 3 : 0, bwd_arrays = ((k1 + k2) % 32 == 0 && k1 % 16 == 0) ? 1 : 0;
+    return plan(k1 + k2, 2 * h, false, fwd_arrays, &s, &b, &c) && plan(2 * h, k1 + k2, false, bwd_arrays, &s, &b, &c);
+}
+
+static NormOp norm_op(const glass_norm_operand* n) {
+    NormOp o{};
+    o.pscale = 1.f;
+    if (n && n->stats) {
+        o.stats = n->stats;
+        o.act = n->act;
+        if (n->drop_p > 0.f) {
+            o.bits = n->bits;
+            o.pscale = 1.f / (1.f - n->drop_p);
+        }
+    }
+    return o;
+}
+
+// Operands normalised on load additionally need: widths that are multiples of 32 (keep-bit words never straddle
+// the a1|a2 boundary or a K-block), the tcgen05 dW kernel (the SIMT kernels read plain operands only), room for
+// the constants next to the resident weights.
+bool pair_tc_norm_supported(int k1, int k2, int h) {
+    if (k1 % 32 || k2 % 32) return false;
+    if (!(h == 64 || h == 128)) return false;
+    const int K = k1 + k2;
+    if (!(K == 32 || K == 64 || K == 96 || K == 128)) return false;
+    int s;
+    size_t b;
+    uint32_t c;
+    return plan(K, 2 * h, true, 3, &s, &b, &c) && s >= 2;
 }
 
 int pair_fwd_tc(const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2, int k2, const float* w0,
                 const float* b0, const float* w1, const float* b1, const uint8_t* mask, float z, int act, float* out,
-                int64_t ldo, float* acts, int64_t n, int h, cudaStream_t st) {
-    if (ldo % 4 || !aligned16(out) || (acts && !aligned16(acts)) || !aligned16(w0) || !aligned16(w1)) {
-        set_error("pair_linear_mix_fwd (tcgen05): outputs / weights must be 16-byte aligned");
+                int64_t ldo, float* acts, int64_t n, int h, const glass_norm_operand* n1, const glass_norm_operand* n2,
+                cudaStream_t st) {
+    if (ldo % 4 || !aligned16(out) || (acts && !aligned16(acts)) || !aligned16(w0) || !aligned16(w1) || !aligned16(b0) ||
+        !aligned16(b1)) {
+        set_error("pair_linear_mix_fwd (tcgen05): outputs / weights / biases must be 16-byte aligned");
         return GLASS_ERR_UNSUPPORTED;
     }
     TcParams P{};
@@ -813,12 +1058,20 @@ int pair_fwd_tc(const float* a1, int64_t lda1, int k1, const float* a2, int64_t 
     P.w0 = w0, P.w1 = w1, P.b0 = b0, P.b1 = b1, P.mask = mask, P.z = z, P.act = act, P.h = h, P.n = n;
     P.out = out, P.ldo = ldo, P.acts = acts;
     P.kdim = k1 + k2, P.ndim = 2 * h;
-    return launch<false>(P, st);
+    P.n1 = norm_op(n1), P.n2 = norm_op(k2 ? n2 : nullptr);
+    if (P.n1.stats || P.n2.stats) {
+        if (!pair_tc_norm_supported(k1, k2, h)) {
+            set_error("pair_linear_mix_fwd (tcgen05): normalised operands need k1, k2 %% 32 == 0 and h in {64, 128}");
+            return GLASS_ERR_UNSUPPORTED;
+        }
+        return launch<false, true>(P, st);
+    }
+    return launch<false, false>(P, st);
 }
 
 int pair_bwd_dx_tc(const float* dout, int64_t lddo, const float* acts, const float* w0, const float* w1,
                    const uint8_t* mask, float z, int act, float* da1, int64_t ldda1, int k1, float* da2, int64_t ldda2,
-                   int k2, int64_t n, int h, cudaStream_t st) {
+                   int k2, int64_t n, int h, int acc1, int acc2, cudaStream_t st) {
     if (lddo % 4 || !aligned16(dout) || (acts && !aligned16(acts)) || (da1 && (ldda1 % 4 || !aligned16(da1))) ||
         (da2 && (ldda2 % 4 || !aligned16(da2)))) {
         set_error("pair_linear_mix_bwd (tcgen05): operands must be 16-byte aligned");
@@ -829,7 +1082,8 @@ int pair_bwd_dx_tc(const float* dout, int64_t lddo, const float* acts, const flo
     P.dout = dout, P.lddo = lddo, P.acts = const_cast<float*>(acts);
     P.da1 = da1, P.ldda1 = ldda1, P.da2 = da2, P.ldda2 = ldda2;
     P.kdim = 2 * h, P.ndim = k1 + k2;
-    return launch<true>(P, st);
+    P.acc1 = acc1, P.acc2 = acc2;
+    return launch<true, false>(P, st);
 }
 
 
@@ -854,7 +1108,8 @@ size_t pair_dw_tc_workspace_bytes(int64_t n, int h, int k) {
 
 int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const float* a1, int64_t lda1, int k1,
                    const float* a2, int64_t lda2, int k2, const uint8_t* mask, float z, int act, float* dw0, float* db0,
-                   float* dw1, float* db1, int64_t n, int h, void* workspace, cudaStream_t st) {
+                   float* dw1, float* db1, int64_t n, int h, void* workspace, const glass_norm_operand* n1,
+                   const glass_norm_operand* n2, cudaStream_t st) {
     if (lddo % 4 || !aligned16(dout) || (acts && !aligned16(acts)) || !aligned16(workspace)) {
         set_error("pair_linear_mix_bwd dW (tcgen05): operands must be 16-byte aligned");
         return GLASS_ERR_UNSUPPORTED;
@@ -868,7 +1123,13 @@ int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const flo
     P.rows_per_cta = dw_tc_rows_per_cta(n);
     const int splits = (int)ceil_div(n, P.rows_per_cta);
     const size_t stage_bytes = 2 * (size_t)128 * 128 + 2 * (size_t)K * 128;
-    const size_t fixed = 1024 + 256 + 16 * 128 * sizeof(float);
+    P.n1 = norm_op(n1), P.n2 = norm_op(k2 ? n2 : nullptr);
+    const bool norm = P.n1.stats || P.n2.stats;
+    if (norm && (k1 % 32 || k2 % 32)) {
+        set_error("pair_linear_mix_bwd dW (tcgen05): normalised operands need k1, k2 %% 32 == 0");
+        return GLASS_ERR_UNSUPPORTED;
+    }
+    const size_t fixed = 1024 + 256 + 16 * 128 * sizeof(float) + (norm ? 16 + (size_t)3 * K * sizeof(float) : 0);
     int stages = (int)(((size_t)kMaxSmem - fixed) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) {
@@ -881,11 +1142,13 @@ int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const flo
     P.tmem_cols = cols;
     static bool attr_done = false;
     if (!attr_done) {
-        GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_done = true;
     }
     dim3 grid((unsigned)splits, (unsigned)(2 * h / 128));
-    k_pair_dw_tc<<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
+    if (norm) k_pair_dw_tc<true><<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
+    else k_pair_dw_tc<false><<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
     const int64_t total = 2 * (int64_t)h * (K + 1);
     k_pair_dw_tc_reduce<<<(unsigned)ceil_div(total, 32), 256, 0, st>>>(P.part, splits, h, K, P.part_ld, dw0, db0, dw1, db1);

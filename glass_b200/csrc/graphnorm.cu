@@ -35,7 +35,8 @@ enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4, ST_RNG = 5 
 // CUDA-graph replay draws fresh ones -- no mask tensor is written or read.
 struct Drop {
     const uint8_t* keep;                 // explicit mask [n, c] or NULL
-    const unsigned long long* rng;       // {seed, call counter} in device memory or NULL
+    const unsigned long long* rng;       // {seed, call counter, ticket} in device memory or NULL (bits drawn in-kernel)
+    const uint32_t* bits;                // packed keep bits (bit r*c + col), written once per call by the finalize kernel
     float pscale;                        // 1 / (1 - p)
     uint32_t thresh;                     // drop iff u32 < thresh  (thresh = p * 2^32)
 };
@@ -72,6 +73,11 @@ __device__ __forceinline__ void drop_mult(const Drop& d, const DropCtx& x, int64
     if (d.keep) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) m[k] = d.keep[lin + k] ? d.pscale : 0.f;
+    } else if (d.bits) {
+        // VEC == 4: lin % 4 == 0 (c % 4 == 0), so the four bits never straddle a word
+        const uint32_t w = __ldg(d.bits + (lin >> 5)) >> (uint32_t)(lin & 31);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) m[k] = ((w >> k) & 1u) ? d.pscale : 0.f;
     } else if (d.rng) {
         const uint64_t grp = (uint64_t)lin >> 2;
         const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), x.call_lo, x.call_hi), x.key);
@@ -99,24 +105,29 @@ struct Fin {
     float* dmean_scale;
 };
 
-__device__ __forceinline__ void reduce_partials(const double* partial, int nblk, int c, int col, double& s, double& q) {
+// Partial sums live in a column-major table: partial[(which * c + col) * ldp + blk], which = 0 (sum / S1) or
+// 1 (sum of squares / S2), so that the warp that finalises a column reads its partials coalesced whoever
+// produced them (k_colsums: <= 296 blocks; the SpMM / pair-GEMM epilogues: one per CTA of their grids).
+__device__ __forceinline__ void reduce_partials(const double* partial, int nblk, int ldp, int c, int col, double& s,
+                                                double& q) {
     const int lane = threadIdx.x & 31;
-    double vs[(kMaxPartialCtas + 31) / 32], vq[(kMaxPartialCtas + 31) / 32];
+    const double* ps = partial + (int64_t)col * ldp;
+    const double* pq = partial + ((int64_t)c + col) * ldp;
+    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+    int i = lane;
+    for (; i + 96 < nblk; i += 128) {             // four independent loads per array in flight
 #pragma unroll
-    for (int i = 0; i < (kMaxPartialCtas + 31) / 32; ++i) {
-        const int b = lane + 32 * i;
-        vs[i] = b < nblk ? __ldcg(partial + ((int64_t)b * 2 + 0) * c + col) : 0.0;
-        vq[i] = b < nblk ? __ldcg(partial + ((int64_t)b * 2 + 1) * c + col) : 0.0;
+        for (int u = 0; u < 4; ++u) {
+            a[u] += __ldcg(ps + i + 32 * u);
+            b[u] += __ldcg(pq + i + 32 * u);
+        }
     }
-    s = 0.0;
-    q = 0.0;
-#pragma unroll
-    for (int i = 0; i < (kMaxPartialCtas + 31) / 32; ++i) {
-        s += vs[i];
-        q += vq[i];
+    for (; i < nblk; i += 32) {
+        a[0] += __ldcg(ps + i);
+        b[0] += __ldcg(pq + i);
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
+    s = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
+    q = warp_sum((b[0] + b[1]) + (b[2] + b[3]));
 }
 
 __device__ __forceinline__ void finalize_fwd_col(const Fin& f, double s, double q, int64_t n, int c, int col) {
@@ -157,7 +168,7 @@ template <int VEC, bool BWD>
 __global__ void __launch_bounds__(kSumThreads)
 k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dout, int64_t lddo,
           const float* __restrict__ stats, const float* __restrict__ bias, int act, const Drop drop, int64_t n, int c,
-          double* __restrict__ partial) {
+          double* __restrict__ partial, int ldp) {
     const DropCtx dctx = BWD ? drop_ctx(drop, stats, c) : DropCtx{};
     // thread -> (column vector cvl, row lane rl).  CVB column vectors are processed per pass.
     const int CV = (c + VEC - 1) / VEC;
@@ -240,30 +251,70 @@ k_colsums(const float* __restrict__ x, int64_t ldx, const float* __restrict__ do
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 if (cv * VEC + k >= c) continue;
-                partial[((int64_t)blockIdx.x * 2 + 0) * c + cv * VEC + k] = sm[0][cvl * VEC + k];
-                partial[((int64_t)blockIdx.x * 2 + 1) * c + cv * VEC + k] = sm[1][cvl * VEC + k];
+                partial[(int64_t)(cv * VEC + k) * ldp + blockIdx.x] = sm[0][cvl * VEC + k];
+                partial[((int64_t)c + cv * VEC + k) * ldp + blockIdx.x] = sm[1][cvl * VEC + k];
             }
         }
         __syncthreads();
     }
 }
 
+// Finalisation (+ dropout bits).  Warp w of the grid finalises column w (when w < c).  With `bits` the same launch
+// also draws this call's keep bits: word i holds elements 32 i .. 32 i + 31 (row-major element index), bit set =
+// keep, drawn exactly like the in-kernel generator (Philox counter = element index / 4, word = index % 4), so
+// every later consumer -- apply, the pair-GEMM operand loaders, backward -- reads one bit instead of running
+// Philox again.  The call id is rng[1]; every CTA reads it first and the last CTA to finish advances it
+// (ticket in rng[2]), so a CUDA-graph replay draws fresh bits.
 template <bool BWD>
-__global__ void __launch_bounds__(128) k_gn_finalize(const double* partial, int nblk, int64_t n, int c, const Fin fin,
-                                                     unsigned long long* rng) {
-    if (!BWD && rng && blockIdx.x == 0 && threadIdx.x == 0) {   // id of this call for the dropout generator
-        const unsigned long long id = rng[1];
-        rng[1] = id + 1;
-        fin.stats[ST_RNG * c + 0] = __uint_as_float((uint32_t)id);
-        if (c > 1) fin.stats[ST_RNG * c + 1] = __uint_as_float((uint32_t)(id >> 32));
+__global__ void __launch_bounds__(256) k_gn_finalize(const double* partial, int nblk, int ldp, int64_t n, int c,
+                                                     const Fin fin, unsigned long long* rng, uint32_t* bits,
+                                                     int64_t n_words, uint32_t thresh) {
+    unsigned long long id = 0, seed = 0;
+    if (!BWD && rng) {
+        seed = rng[0];
+        id = *reinterpret_cast<volatile unsigned long long*>(rng + 1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            fin.stats[ST_RNG * c + 0] = __uint_as_float((uint32_t)id);
+            if (c > 1) fin.stats[ST_RNG * c + 1] = __uint_as_float((uint32_t)(id >> 32));
+        }
     }
     const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (col >= c) return;
-    double a, b;
-    reduce_partials(partial, nblk, c, col, a, b);
-    if ((threadIdx.x & 31) != 0) return;
-    if (BWD) finalize_bwd_col(fin, a, b, n, c, col);
-    else finalize_fwd_col(fin, a, b, n, c, col);
+    if (col < c) {
+        double a, b;
+        reduce_partials(partial, nblk, ldp, c, col, a, b);
+        if ((threadIdx.x & 31) == 0) {
+            if (BWD) finalize_bwd_col(fin, a, b, n, c, col);
+            else finalize_fwd_col(fin, a, b, n, c, col);
+        }
+    }
+    if (!BWD && rng) {
+        if (bits) {
+            const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+            const uint32_t call_lo = (uint32_t)id, call_hi = c > 1 ? (uint32_t)(id >> 32) : 0u;   // as drop_ctx() reads it back
+            for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint64_t grp = (uint64_t)w * 8 + g;
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), call_lo, call_hi), key);
+                    word |= (r.x < thresh ? 0u : 1u) << (4 * g);
+                    word |= (r.y < thresh ? 0u : 1u) << (4 * g + 1);
+                    word |= (r.z < thresh ? 0u : 1u) << (4 * g + 2);
+                    word |= (r.w < thresh ? 0u : 1u) << (4 * g + 3);
+                }
+                bits[w] = word;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned* ticket = reinterpret_cast<unsigned*>(rng + 2);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+                rng[1] = id + 1;
+                *ticket = 0u;
+            }
+        }
+    }
 }
 
 constexpr int kApplyCtasPerSm = 4, kBwdApplyCtasPerSm = 3;   // resident CTAs (registers); grids are one wave
@@ -312,7 +363,8 @@ k_gn_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ s
     }
 }
 
-template <int VEC>
+// PREMASKED: `dout` already is u = dout * keep/(1-p) * act'(pre) (formed by the producer of the gradient).
+template <int VEC, bool PREMASKED>
 __global__ void __launch_bounds__(kThreads, kBwdApplyCtasPerSm)
 k_gn_bwd_apply(const float* __restrict__ dout, int64_t lddo, const float* __restrict__ x, int64_t ldx,
                const float* __restrict__ stats, const float* __restrict__ bias, const float* __restrict__ coef, int act,
@@ -350,11 +402,11 @@ k_gn_bwd_apply(const float* __restrict__ dout, int64_t lddo, const float* __rest
                 gv[0] = dout[r * lddo + col];
             }
             float dm[VEC];
-            drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
+            if (!PREMASKED) drop_mult<VEC>(drop, dctx, r * (int64_t)c + col, dm);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 const float o = xv[k] - am[k];
-                const float u = gv[k] * act_grad_from_pre(fmaf(sc[k], o, bs[k]), act) * dm[k];
+                const float u = PREMASKED ? gv[k] : gv[k] * act_grad_from_pre(fmaf(sc[k], o, bs[k]), act) * dm[k];
                 ov[k] = fmaf(c0[k], u, fmaf(c1[k], o * rs[k], c2[k]));
             }
             if (VEC == 4) *reinterpret_cast<float4*>(dx + r * lddx + col) = make_float4(ov[0], ov[1], ov[2], ov[3]);
@@ -569,20 +621,21 @@ inline bool use_cluster(int64_t n, int c, int vec) {
     return c <= kClMaxC && (c + vec - 1) / vec <= kClThreads && n * (int64_t)c <= max_elems;
 }
 
-inline Drop make_drop(const uint8_t* keep, const unsigned long long* rng, float p) {
+inline Drop make_drop(const uint8_t* keep, const unsigned long long* rng, const uint32_t* bits, float p) {
     Drop d{};
     d.pscale = 1.f;
     if (p > 0.f) {
         d.pscale = 1.f / (1.f - p);
+        double t = (double)p * 4294967296.0;
+        d.thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
         if (keep) d.keep = keep;
-        else if (rng) {
-            d.rng = rng;
-            double t = (double)p * 4294967296.0;
-            d.thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
-        }
+        else if (bits) d.bits = bits;
+        else if (rng) d.rng = rng;
     }
     return d;
 }
+
+constexpr int kPartialLd = 320;   // leading dimension of the internal partial table (k_colsums: <= 296 blocks)
 
 inline int partial_ctas(int64_t n, int c, int vec) {
     int cv = (c + vec - 1) / vec;
@@ -602,6 +655,33 @@ inline bool vec_ok(int c, std::initializer_list<int64_t> lds, std::initializer_l
     return true;
 }
 
+inline size_t partial_bytes(int c) { return align_up((size_t)2 * (size_t)c * kPartialLd * sizeof(double), 256); }
+
+// finalize (forward) + this call's dropout bits in one launch
+int launch_finalize_fwd(const double* partial, int nblk, int ldp, int64_t n, int c, const Fin& fin, const Drop& drop,
+                        unsigned long long* rng, uint32_t* bits, cudaStream_t st) {
+    const bool draw = drop.pscale != 1.f && !drop.keep && rng;          // bits (or the call id) come from the generator
+    uint32_t* out_bits = (draw && drop.bits) ? bits : nullptr;
+    const int64_t n_words = out_bits ? ceil_div(n * (int64_t)c, 32) : 0;
+    int64_t grid = ceil_div(c, 8);
+    if (out_bits) grid = std::max<int64_t>(grid, std::min<int64_t>(ceil_div(n_words, 256), (int64_t)sm_count() * 4));
+    k_gn_finalize<false><<<(unsigned)grid, 256, 0, st>>>(partial, nblk, ldp, n, c, fin, draw ? rng : nullptr, out_bits,
+                                                        n_words, drop.thresh);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
+int launch_apply(const float* x, int64_t ldx, const float* stats, int act, const Drop& drop, float* out, int64_t ldo,
+                 int64_t n, int c, cudaStream_t st) {
+    const float* bias = stats + ST_BIAS * (int64_t)c;
+    const bool vec = vec_ok(c, {ldx, ldo}, {x, out});
+    const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kApplyCtasPerSm);
+    if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
+    else k_gn_apply<1><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
 }  // namespace
 }  // namespace glass
 
@@ -609,7 +689,7 @@ using namespace glass;
 
 extern "C" size_t glass_graphnorm_workspace_bytes(int64_t n, int c) {
     if (n < 0 || c <= 0) return 0;
-    return align_up((size_t)kMaxPartialCtas * 2 * (size_t)c * sizeof(double), 256) + align_up(3 * (size_t)c * sizeof(float), 256);
+    return partial_bytes(c) + align_up(3 * (size_t)c * sizeof(float), 256);
 }
 
 extern "C" int glass_graphnorm_launches(int64_t n, int c) {
@@ -617,10 +697,15 @@ extern "C" int glass_graphnorm_launches(int64_t n, int c) {
     return use_cluster(n, c, c % 4 == 0 ? 4 : 1) ? 1 : 3;
 }
 
+extern "C" size_t glass_dropout_bits_bytes(int64_t n, int c) {
+    if (n < 0 || c <= 0) return 0;
+    return (size_t)ceil_div(n * (int64_t)c, 32) * sizeof(uint32_t);
+}
+
 extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                                    const float* mean_scale, float eps, int act, const uint8_t* keep, float drop_p,
-                                   unsigned long long* rng, float* out, int64_t ldo, float* stats, int64_t n, int c,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   unsigned long long* rng, uint32_t* bits, float* out, int64_t ldo, float* stats,
+                                   int64_t n, int c, void* workspace, size_t workspace_bytes, void* stream) {
     GLASS_CHECK_ARG(x && weight && bias && mean_scale && out && stats && n > 0 && c > 0 && ldx >= c && ldo >= c,
                     "graphnorm_fwd: bad arguments");
     if (workspace_bytes < glass_graphnorm_workspace_bytes(n, c) || !workspace) {
@@ -634,29 +719,52 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
     Fin fin{};
     fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats;
     GLASS_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "graphnorm_fwd: dropout p must be in [0, 1)");
-    if (use_cluster(n, c, vec ? 4 : 1)) {
-        const Drop d = make_drop(keep, rng, drop_p);
+    if (use_cluster(n, c, vec ? 4 : 1)) {   // tiny matrix: one launch, bits drawn in-kernel (the `bits` buffer stays unused)
+        const Drop d = make_drop(keep, rng, nullptr, drop_p);
         if (vec) k_gn_cluster<4, false><<<kCl, kClThreads, 0, st>>>(x, ldx, nullptr, 0, fin, act, d, rng, out, ldo, n, c);
         else k_gn_cluster<1, false><<<kCl, kClThreads, 0, st>>>(x, ldx, nullptr, 0, fin, act, d, rng, out, ldo, n, c);
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
     }
-    if (vec) k_colsums<4, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
-    else k_colsums<1, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial);
-    const Drop drop = make_drop(keep, rng, drop_p);
-    k_gn_finalize<false><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, drop.rng ? rng : nullptr);
-    const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kApplyCtasPerSm);
-    if (vec) k_gn_apply<4><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
-    else k_gn_apply<1><<<grid, kThreads, 0, st>>>(x, ldx, stats, bias, act, drop, out, ldo, n, c);
-    GLASS_LAUNCH_CHECK();
-    return GLASS_OK;
+    if (vec) k_colsums<4, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial, kPartialLd);
+    else k_colsums<1, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial, kPartialLd);
+    const Drop drop = make_drop(keep, rng, bits, drop_p);
+    int rc = launch_finalize_fwd(partial, nblk, kPartialLd, n, c, fin, drop, rng, bits, st);
+    if (rc != GLASS_OK) return rc;
+    return launch_apply(x, ldx, stats, act, drop, out, ldo, n, c, st);
+}
+
+// Statistics produced elsewhere (the SpMM epilogue, the pair-GEMM epilogue): partial[(which * c + col) * ldp + blk],
+// blk < nblk.  Writes `stats` (and draws the dropout bits of this call); the normalisation itself is applied by
+// whoever consumes x next (glass_graphnorm_apply, or the operand loader of glass_pair_linear_mix_*_ex).
+extern "C" int glass_graphnorm_stats(const double* partial, int nblk, int ldp, const float* weight, const float* bias,
+                                     const float* mean_scale, float eps, const uint8_t* keep, float drop_p,
+                                     unsigned long long* rng, uint32_t* bits, float* stats, int64_t n, int c,
+                                     void* stream) {
+    GLASS_CHECK_ARG(partial && nblk > 0 && ldp >= nblk && weight && bias && mean_scale && stats && n > 0 && c > 0,
+                    "graphnorm_stats: bad arguments");
+    GLASS_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "graphnorm_stats: dropout p must be in [0, 1)");
+    GLASS_CHECK_ARG(!(drop_p > 0.f && !keep && rng && !bits), "graphnorm_stats: generator dropout needs a bits buffer");
+    Fin fin{};
+    fin.weight = weight, fin.bias = bias, fin.mean_scale = mean_scale, fin.eps = eps, fin.stats = stats;
+    const Drop drop = make_drop(keep, rng, bits, drop_p);
+    return launch_finalize_fwd(partial, nblk, ldp, n, c, fin, drop, rng, bits, as_stream(stream));
+}
+
+extern "C" int glass_graphnorm_apply(const float* x, int64_t ldx, const float* stats, int act, const uint8_t* keep,
+                                     float drop_p, const uint32_t* bits, float* out, int64_t ldo, int64_t n, int c,
+                                     void* stream) {
+    GLASS_CHECK_ARG(x && stats && out && n > 0 && c > 0 && ldx >= c && ldo >= c, "graphnorm_apply: bad arguments");
+    GLASS_CHECK_ARG(!(drop_p > 0.f && !keep && !bits), "graphnorm_apply: dropout needs a keep mask or packed bits");
+    const Drop drop = make_drop(keep, nullptr, bits, drop_p);
+    return launch_apply(x, ldx, stats, act, drop, out, ldo, n, c, as_stream(stream));
 }
 
 extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* weight,
                                    const float* mean_scale, const float* stats, int act, const uint8_t* keep,
-                                   float drop_p, const unsigned long long* rng, float* dx, int64_t lddx, float* dweight, float* dbias,
-                                   float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+                                   float drop_p, const unsigned long long* rng, const uint32_t* bits, float* dx,
+                                   int64_t lddx, float* dweight, float* dbias, float* dmean_scale, int64_t n, int c,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
     GLASS_CHECK_ARG(dout && x && weight && mean_scale && stats && dx && dweight && dbias && dmean_scale && n > 0 &&
                         c > 0 && ldx >= c && lddo >= c && lddx >= c,
                     "graphnorm_bwd: bad arguments");
@@ -666,27 +774,58 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
     }
     cudaStream_t st = as_stream(stream);
     double* partial = static_cast<double*>(workspace);
-    float* coef = reinterpret_cast<float*>(static_cast<char*>(workspace) +
-                                           align_up((size_t)kMaxPartialCtas * 2 * (size_t)c * sizeof(double), 256));
+    float* coef = reinterpret_cast<float*>(static_cast<char*>(workspace) + partial_bytes(c));
     const float* bias = stats + ST_BIAS * (int64_t)c;  // forward bias saved with the statistics
     const bool vec = vec_ok(c, {ldx, lddo, lddx}, {x, dout, dx});
     const int nblk = partial_ctas(n, c, vec ? 4 : 1);
     Fin fin{};
     fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
     fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale;
-    const Drop drop = make_drop(keep, rng, drop_p);
     if (use_cluster(n, c, vec ? 4 : 1)) {
+        const Drop drop = make_drop(keep, rng, nullptr, drop_p);
         if (vec) k_gn_cluster<4, true><<<kCl, kClThreads, 0, st>>>(x, ldx, dout, lddo, fin, act, drop, nullptr, dx, lddx, n, c);
         else k_gn_cluster<1, true><<<kCl, kClThreads, 0, st>>>(x, ldx, dout, lddo, fin, act, drop, nullptr, dx, lddx, n, c);
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
     }
-    if (vec) k_colsums<4, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
-    else k_colsums<1, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial);
-    k_gn_finalize<true><<<(unsigned)ceil_div(c, 4), 128, 0, st>>>(partial, nblk, n, c, fin, nullptr);
+    const Drop drop = make_drop(keep, rng, bits, drop_p);
+    if (vec) k_colsums<4, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial, kPartialLd);
+    else k_colsums<1, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial, kPartialLd);
+    k_gn_finalize<true><<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nblk, kPartialLd, n, c, fin, nullptr, nullptr, 0, 0u);
     const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kBwdApplyCtasPerSm);
-    if (vec) k_gn_bwd_apply<4><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
-    else k_gn_bwd_apply<1><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
+    if (vec) k_gn_bwd_apply<4, false><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
+    else k_gn_bwd_apply<1, false><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
+// Backward when the producer of the gradient (the dX epilogue of the pair GEMM) has already formed
+// u = dout * keep/(1-p) * act'(pre) and the per-CTA partial sums of S1 = sum u, S2 = sum u * yhat:
+// finalise + one element-wise pass dx = alpha u + beta yhat + gamma.  `u` and `dx` may alias.
+extern "C" int glass_graphnorm_bwd_from_sums(const double* partial, int nblk, int ldp, const float* u, int64_t ldu,
+                                             const float* x, int64_t ldx, const float* weight, const float* mean_scale,
+                                             const float* stats, float* dx, int64_t lddx, float* dweight, float* dbias,
+                                             float* dmean_scale, int64_t n, int c, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+    GLASS_CHECK_ARG(partial && nblk > 0 && ldp >= nblk && u && x && weight && mean_scale && stats && dx && dweight &&
+                        dbias && dmean_scale && n > 0 && c > 0 && ldu >= c && ldx >= c && lddx >= c,
+                    "graphnorm_bwd_from_sums: bad arguments");
+    if (workspace_bytes < align_up(3 * (size_t)c * sizeof(float), 256) || !workspace) {
+        set_error("graphnorm_bwd_from_sums: workspace too small");
+        return GLASS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    float* coef = static_cast<float*>(workspace);
+    const float* bias = stats + ST_BIAS * (int64_t)c;
+    Fin fin{};
+    fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
+    fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale;
+    k_gn_finalize<true><<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nblk, ldp, n, c, fin, nullptr, nullptr, 0, 0u);
+    const bool vec = vec_ok(c, {ldx, ldu, lddx}, {x, u, dx});
+    const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kBwdApplyCtasPerSm);
+    const Drop none{};
+    if (vec) k_gn_bwd_apply<4, true><<<grid, kThreads, 0, st>>>(u, ldu, x, ldx, stats, bias, coef, GLASS_ACT_NONE, none, dx, lddx, n, c);
+    else k_gn_bwd_apply<1, true><<<grid, kThreads, 0, st>>>(u, ldu, x, ldx, stats, bias, coef, GLASS_ACT_NONE, none, dx, lddx, n, c);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

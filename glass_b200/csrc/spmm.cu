@@ -14,6 +14,7 @@
 // (em_user shape): 5 resident CTAs per SM (48 registers) 131 us; 3 / 6 / 8 CTAs 141 / 143 / 150 us; deeper
 // unrolling with fewer CTAs 205-225 us; L1::no_allocate gathers 156 us.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -63,10 +64,11 @@ struct RowWork {
     const int32_t* rowptr;
     float* y;
     int64_t ldy;
-    __device__ __forceinline__ void get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
+    __device__ __forceinline__ bool get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
         b = __ldg(rowptr + item);
         e = __ldg(rowptr + item + 1);
         dst = y + item * ldy;
+        return true;                   // a complete row of y
     }
 };
 struct PlanWork {
@@ -77,11 +79,12 @@ struct PlanWork {
     int64_t ldy;
     float* scratch;            // [n_slots, ld_s]
     int64_t ld_s;
-    __device__ __forceinline__ void get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
+    __device__ __forceinline__ bool get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
         b = __ldg(item_begin + item);
         e = __ldg(item_end + item);
         const int32_t d = __ldg(item_dst + item);
         dst = d >= 0 ? y + (int64_t)d * ldy : scratch + (int64_t)(-1 - d) * ld_s;
+        return d >= 0;                 // scratch rows are partial sums of a split row (k_spmm_combine finishes them)
     }
 };
 
@@ -92,10 +95,15 @@ struct PlanWork {
 // for graphs that do not fill the machine, where the longest row's dependent gather chain is the
 // whole kernel time (density: 409-entry row on 2 lanes = 65 us; 16 slots -> see DESIGN.md 4.1).
 // EXACT: h == G*VEC*KCH (no column guards).  IDX32: every element offset into x fits 32 bits.
-template <int G, int S, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, class Work>
+// STATS: the epilogue also emits this CTA's fp64 partial column sums of y and y^2 (the GraphNorm statistics of
+// impl/models.py:165, so that no separate pass over y is needed): partial[(which * h + c) * ldp + blockIdx.x].
+// Every output element is added exactly once, by the thread that stores it, in item order; the lanes / warps
+// of a CTA are combined in a fixed order -> deterministic.  UNR: neighbour gathers in flight per lane.
+template <int G, int S, int VEC, int KCH, bool EXACT, bool IDX32, int MINB, int UNR, bool STATS, class Work>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const int32_t* __restrict__ col,
                                                          const float* __restrict__ val, const float* __restrict__ x,
-                                                         int64_t ldx, int64_t n_items, int h) {
+                                                         int64_t ldx, int64_t n_items, int h,
+                                                         double* __restrict__ partial, int ldp) {
     using V = Vec<VEC>;
     constexpr int GW = G * S;                          // lanes per row
     static_assert(GW <= 32 && (GW & (GW - 1)) == 0, "row group must be a power-of-two part of a warp");
@@ -119,10 +127,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
         colok[k] = EXACT || coff[k] < h;
     }
 
+    // per-thread running sums stay in fp32 (a thread finishes only a handful of rows; fp64 arithmetic in this loop
+    // cost 20 us on the em_user shape), everything above the thread level is added in fp64
+    float st_s[STATS ? KCH * VEC : 1], st_q[STATS ? KCH * VEC : 1];
+#pragma unroll
+    for (int i = 0; i < (STATS ? KCH * VEC : 1); ++i) st_s[i] = st_q[i] = 0.f;
+
     for (; item < n_items; item += groups_per_grid) {
         int32_t e_begin, e_end;
         float* yr;
-        work.get(item, e_begin, e_end, yr);
+        const bool full_row = work.get(item, e_begin, e_end, yr);
         typename V::T acc[KCH];
 #pragma unroll
         for (int k = 0; k < KCH; ++k) acc[k] = V::zero();
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
             }
             __syncwarp(gmask);
             const int2* se = &s_e[buf][gbase];
-#pragma unroll 4
+#pragma unroll UNR
             for (int j = slot; j < cnt; j += S) {
                 const int2 cv = se[j];                                  // broadcast read inside the group
                 const float* xr = IDX32 ? x + (uint32_t)cv.x * ldx32 : x + (int64_t)cv.x * ldx;
@@ -163,20 +177,64 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
 #pragma unroll
             for (int k = 0; k < KCH; ++k)
                 if (colok[k]) V::store(yr + coff[k], acc[k]);
+            if (STATS && full_row) {
+#pragma unroll
+                for (int k = 0; k < KCH; ++k) {
+                    const float* a = reinterpret_cast<const float*>(&acc[k]);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        st_s[k * VEC + v] += a[v];
+                        st_q[k * VEC + v] = fmaf(a[v], a[v], st_q[k * VEC + v]);
+                    }
+                }
+            }
+        }
+    }
+    if (STATS) {
+        // lanes of a warp that own the same columns (same feature lane l), then the warps of the CTA in order
+        __shared__ double s_red[kThreads / 32][G * VEC * KCH];
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int i = 0; i < KCH * VEC; ++i) {
+                double t = (double)(which ? st_q[i] : st_s[i]);
+#pragma unroll
+                for (int off = G; off < 32; off <<= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                if (lane < G) s_red[warp][coff[i / VEC] + (i % VEC)] = t;
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < h; c += kThreads) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < kThreads / 32; ++w) t += s_red[w][c];
+                partial[((int64_t)which * h + c) * ldp + blockIdx.x] = t;
+            }
+            __syncthreads();
         }
     }
 }
 
-// y[long_row[i], :] = sum of its scratch rows, in chunk order (deterministic)
+// y[long_row[i], :] = sum of its scratch rows, in chunk order (deterministic).  A fixed grid walks the long rows;
+// with `partial` the CTAs also emit their column sums of the rows they finish (blocks first_blk .. first_blk+grid-1).
 __global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot,
-                               const int32_t* __restrict__ long_cnt, const float* __restrict__ scratch, int64_t ld_s,
-                               float* __restrict__ y, int64_t ldy, int h) {
-    const int i = blockIdx.x;
-    const int32_t r = long_row[i], s0 = long_slot[i], cnt = long_cnt[i];
+                               const int32_t* __restrict__ long_cnt, int64_t n_long, const float* __restrict__ scratch,
+                               int64_t ld_s, float* __restrict__ y, int64_t ldy, int h, double* __restrict__ partial,
+                               int ldp, int first_blk) {
     for (int c = threadIdx.x; c < h; c += blockDim.x) {
-        float acc = 0.f;
-        for (int k = 0; k < cnt; ++k) acc += scratch[(int64_t)(s0 + k) * ld_s + c];
-        y[(int64_t)r * ldy + c] = acc;
+        double s = 0.0, q = 0.0;
+        for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+            const int32_t r = long_row[i], s0 = long_slot[i], cnt = long_cnt[i];
+            float acc = 0.f;
+            for (int k = 0; k < cnt; ++k) acc += scratch[(int64_t)(s0 + k) * ld_s + c];
+            y[(int64_t)r * ldy + c] = acc;
+            s += (double)acc;
+            q = fma((double)acc, (double)acc, q);
+        }
+        if (partial) {
+            partial[(int64_t)c * ldp + first_blk + blockIdx.x] = s;
+            partial[((int64_t)h + c) * ldp + first_blk + blockIdx.x] = q;
+        }
     }
 }
 
@@ -188,64 +246,104 @@ struct Plan {   // host view of the arguments of glass_spmm_csr_planned
     float* scratch;
 };
 
+struct Stats {   // optional epilogue statistics (GraphNorm column sums)
+    double* partial;
+    int ldp;
+    int* nblk_host;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// tuning knobs (environment at start-up, glass_tune() at run time; measured settings are the defaults)
+static int g_variant = env_int("GLASS_B200_SPMM_VARIANT", 0);
+static int g_waves = env_int("GLASS_B200_SPMM_WAVES", 0);
+
 // Lanes of one full-occupancy wave (148 SMs x 2048 threads on B200): below about two of them the kernel is
 // bound by its longest row, not by gather throughput, and the neighbour-parallel configuration wins.
 static bool latency_regime(int64_t n_items) {
-    static const int force = [] {
-        const char* e = getenv("GLASS_B200_SPMM_SLOTS");   // 0: never, 1: always, unset: by size
-        return e ? atoi(e) : -1;
-    }();
+    static const int force = env_int("GLASS_B200_SPMM_SLOTS", -1);   // 0: never, 1: always, unset: by size
     if (force >= 0) return force != 0;
     return n_items * 32 <= 2ll * sm_count() * 2048;
 }
 
-template <int G, int S, int VEC, int KCH, int MINB = 4>
+constexpr int kCombineCtas = 148;
+
+static int64_t grid_cap(bool stats) {
+    // plain: a few waves of resident CTAs (items are interleaved).  With statistics every CTA leaves a partial
+    // that the finalize kernel has to add, so the grid is kept to about two waves.
+    if (g_waves > 0) return (int64_t)sm_count() * 5 * g_waves;
+    return stats ? (int64_t)sm_count() * 5 * 2 : (int64_t)sm_count() * 8 * 4;
+}
+
+template <int G, int S, int VEC, int KCH, int MINB = 4, int UNR = 4>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
-           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
+           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st) {
     const int64_t n_items = plan ? plan->n_items : n_rows;
     const int64_t groups_per_block = kThreads / (G * S);
     int64_t blocks = ceil_div(n_items, groups_per_block);
-    const int64_t cap = (int64_t)sm_count() * 8 * 4;  // a few waves of resident CTAs; items are interleaved
+    const int64_t cap = grid_cap(stats != nullptr);
     if (blocks > cap) blocks = cap;
     const bool exact = h == G * VEC * KCH;
     const bool idx32 = n_cols * ldx < (1ll << 31);
     const unsigned grid = (unsigned)blocks;
-#define GLASS_SPMM_GO(E, I)                                                                                           \
+    const bool comb = plan && plan->n_long > 0;
+    const int n_comb = comb ? (int)std::min<int64_t>(plan->n_long, kCombineCtas) : 0;
+    double* partial = stats ? stats->partial : nullptr;
+    const int ldp = stats ? stats->ldp : 0;
+    if (stats) {
+        if ((int64_t)grid + n_comb > ldp) {
+            set_error("spmm_csr: statistics table too small (ldp %d < %lld blocks)", ldp, (long long)grid + n_comb);
+            return GLASS_ERR_WORKSPACE;
+        }
+        *stats->nblk_host = (int)grid + n_comb;
+    }
+#define GLASS_SPMM_GO2(E, I, ST)                                                                                      \
     do {                                                                                                              \
         if (plan) {                                                                                                   \
             PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h};          \
-            k_spmm<G, S, VEC, KCH, E, I, MINB, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);    \
+            k_spmm<G, S, VEC, KCH, E, I, MINB, UNR, ST, PlanWork>                                                     \
+                <<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h, partial, ldp);                           \
         } else {                                                                                                      \
             RowWork w{rowptr, y, ldy};                                                                                \
-            k_spmm<G, S, VEC, KCH, E, I, MINB, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h);     \
+            k_spmm<G, S, VEC, KCH, E, I, MINB, UNR, ST, RowWork>                                                      \
+                <<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h, partial, ldp);                           \
         }                                                                                                             \
+    } while (0)
+#define GLASS_SPMM_GO(E, I)                                                                                           \
+    do {                                                                                                              \
+        if (stats) GLASS_SPMM_GO2(E, I, true);                                                                        \
+        else GLASS_SPMM_GO2(E, I, false);                                                                             \
     } while (0)
     if (exact && idx32) GLASS_SPMM_GO(true, true);
     else if (exact) GLASS_SPMM_GO(true, false);
     else if (idx32) GLASS_SPMM_GO(false, true);
     else GLASS_SPMM_GO(false, false);
 #undef GLASS_SPMM_GO
+#undef GLASS_SPMM_GO2
     GLASS_LAUNCH_CHECK();
-    if (plan && plan->n_long > 0) {
+    if (comb) {
         const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
-        k_spmm_combine<<<(unsigned)plan->n_long, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt,
-                                                                 plan->scratch, (int64_t)h, y, ldy, h);
+        k_spmm_combine<<<(unsigned)n_comb, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long,
+                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, (int)grid);
         GLASS_LAUNCH_CHECK();
     }
     return GLASS_OK;
 }
 
 int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
-             int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, cudaStream_t st) {
+             int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st) {
     const bool vec = (h % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
                      ((uintptr_t)y % 16 == 0) && (!plan || (uintptr_t)plan->scratch % 16 == 0);
     const int64_t n_items = plan ? plan->n_items : n_rows;
     const bool par = latency_regime(n_items);
+#define ARGS rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, stats, st
 #define GO(G, V, K)                                                                                                   \
     do {                                                                                                              \
-        if (par && G < 32)                                                                                            \
-            return launch<G, 32 / G, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);            \
-        return launch<G, 1, V, K>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);                     \
+        if (par && G < 32) return launch<G, 32 / G, V, K>(ARGS);                                                      \
+        return launch<G, 1, V, K>(ARGS);                                                                              \
     } while (0)
     if (vec) {
         const int lanes = h / 4;
@@ -253,8 +351,19 @@ int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const 
         if (lanes <= 4) GO(4, 4, 1);
         if (lanes <= 8) GO(8, 4, 1);
         if (lanes <= 16) {
-            if (par) return launch<16, 2, 4, 1>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);
-            return launch<16, 1, 4, 1, 5>(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, st);
+            if (par) return launch<16, 2, 4, 1>(ARGS);
+            // throughput configuration of the 64-wide layers.  GLASS_B200_SPMM_VARIANT selects tuning variants
+            // (gathers in flight per lane / resident CTAs per SM / lanes per row); measured numbers in DESIGN.md 4.1
+            switch (g_variant) {
+                case 1: return launch<16, 1, 4, 1, 4, 8>(ARGS);
+                case 2: return launch<8, 1, 4, 2, 5, 4>(ARGS);
+                case 3: return launch<8, 1, 4, 2, 4, 4>(ARGS);
+                case 4: return launch<8, 1, 4, 2, 3, 8>(ARGS);
+                case 5: return launch<16, 1, 4, 1, 6, 4>(ARGS);
+                case 6: return launch<16, 1, 4, 1, 3, 8>(ARGS);
+                case 7: return launch<16, 1, 4, 1, 4, 4>(ARGS);
+                default: return launch<16, 1, 4, 1, 5, 4>(ARGS);
+            }
         }
         if (lanes <= 32) GO(32, 4, 1);
         GO(32, 4, 2);
@@ -268,6 +377,7 @@ int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const 
         GO(32, 1, 8);
     }
 #undef GO
+#undef ARGS
 }
 
 }  // namespace
@@ -275,13 +385,37 @@ int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const 
 
 using namespace glass;
 
+// Run-time tuning knobs of the SpMM dispatcher (benchmark scripts): "spmm_variant", "spmm_waves".
+extern "C" int glass_tune(const char* name, int value) {
+    GLASS_CHECK_ARG(name, "tune: null name");
+    if (!strcmp(name, "spmm_variant")) g_variant = value;
+    else if (!strcmp(name, "spmm_waves")) g_waves = value;
+    else {
+        set_error("tune: unknown knob %s", name);
+        return GLASS_ERR_BAD_ARG;
+    }
+    return GLASS_OK;
+}
+
+// Upper bound of the statistics blocks a SpMM launch can produce (leading dimension of the partial table).
+extern "C" int glass_spmm_stats_ld(void) {
+    const int n = sm_count();
+    if (n <= 0) return 0;
+    return (int)align_up((size_t)sm_count() * 8 * 4 + kCombineCtas, 32);   // >= any grid the dispatcher launches
+}
+
 extern "C" int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
-                              int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h, void* stream) {
+                              int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h,
+                              double* stats_partial, int stats_ld, int* stats_nblk_host, void* stream) {
     GLASS_CHECK_ARG(rowptr && x && y && n_rows >= 0 && n_cols > 0 && h > 0 && ldx >= h && ldy >= h,
                     "spmm_csr: bad arguments");
     GLASS_CHECK_ARG(h <= 256, "spmm_csr: h=%d > 256 not supported", h);
+    GLASS_CHECK_ARG(!stats_partial || (stats_ld > 0 && stats_nblk_host), "spmm_csr: statistics arguments incomplete");
+    if (stats_nblk_host) *stats_nblk_host = 0;
     if (n_rows == 0) return GLASS_OK;
-    return dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, nullptr, as_stream(stream));
+    Stats s{stats_partial, stats_ld, stats_nblk_host};
+    return dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, nullptr, stats_partial ? &s : nullptr,
+                    as_stream(stream));
 }
 
 // ---- row-splitting plan (init path; reads rowptr back to the host) ------------------------------------
@@ -364,12 +498,17 @@ extern "C" int glass_spmm_csr_planned(const int32_t* col, const float* val, cons
                                       int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const int32_t* item_begin,
                                       const int32_t* item_end, const int32_t* item_dst, int64_t n_items,
                                       const int32_t* long_row, const int32_t* long_slot, const int32_t* long_cnt,
-                                      int64_t n_long, float* scratch, void* stream) {
+                                      int64_t n_long, float* scratch, double* stats_partial, int stats_ld,
+                                      int* stats_nblk_host, void* stream) {
     GLASS_CHECK_ARG(col && val && x && y && n_rows >= 0 && n_cols > 0 && h > 0 && ldx >= h && ldy >= h && item_begin &&
                         item_end && item_dst && n_items >= n_rows && (n_long == 0 || (long_row && long_slot && long_cnt && scratch)),
                     "spmm_csr_planned: bad arguments");
     GLASS_CHECK_ARG(h <= 256, "spmm_csr_planned: h=%d > 256 not supported", h);
+    GLASS_CHECK_ARG(!stats_partial || (stats_ld > 0 && stats_nblk_host), "spmm_csr_planned: statistics arguments incomplete");
+    if (stats_nblk_host) *stats_nblk_host = 0;
     if (n_items == 0) return GLASS_OK;
     Plan p{item_begin, item_end, item_dst, n_items, long_row, long_slot, long_cnt, n_long, scratch};
-    return dispatch(nullptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, &p, as_stream(stream));
+    Stats s{stats_partial, stats_ld, stats_nblk_host};
+    return dispatch(nullptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, &p, stats_partial ? &s : nullptr,
+                    as_stream(stream));
 }

@@ -110,11 +110,19 @@ class GLASSConv(nn.Module):
             self.adj = buildAdj(edge_index, edge_weight, x_.shape[0], self.aggr)
         m = _mask_u8(mask)
         t0, t1 = self.trans_fns
+        c0, c1 = self.comb_fns
+        gn = self.gn
+        if x_.is_cuda and x_.dim() == 2 and ops.conv_fusable(x_.shape[1], t0.weight.shape[0]):
+            # the whole layer as one fused chain (tcgen05 shapes): ops._GlassConv
+            return ops.glass_conv(x_, self.adj, (t0.weight, t0.bias, t1.weight, t1.bias),
+                                  (gn.weight, gn.bias, gn.mean_scale, gn.eps),
+                                  (c0.weight, c0.bias, c1.weight, c1.bias), m, self.z_ratio,
+                                  _act_id(self.activation), self.dropout, self.training)
         x = ops.pair_linear_mix(x_, None, t0.weight, t0.bias, t1.weight, t1.bias, m, self.z_ratio,
                                 _act_id(self.activation))                                   # :158-162
-        x = ops.spmm(self.adj, x)                                                           # :164
-        x = self.gn(x, p=self.dropout, training=self.training)                              # :165-166
-        c0, c1 = self.comb_fns
+        # :164-166, one fused op
+        x = ops.spmm_graph_norm(self.adj, x, gn.weight, gn.bias, gn.mean_scale, gn.eps, ACT_NONE, self.dropout,
+                                self.training)
         return ops.pair_linear_mix(x, x_, c0.weight, c0.bias, c1.weight, c1.bias, m, self.z_ratio,
                                    ACT_NONE)                                                # :167-173
 

@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
 
-__all__ = ["CSRAdj", "build_csr", "spmm", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
+__all__ = ["CSRAdj", "build_csr", "spmm", "spmm_graph_norm", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
            "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",
            "set_gemm_path", "launch_count", "reset_launch_count", "manual_seed"]
 
@@ -91,30 +91,40 @@ def _define(schema: str, fn):
     _L.impl(schema.split("(")[0], fn, "CUDA")
 
 
-def _spmm_csr_(rowptr, col, val, x, y):
+def _spmm_csr_(rowptr, col, val, x, y, partial):
+    """partial: optional fp64 [2*h, ld] table that receives the per-CTA column sums of y and y^2 (GraphNorm
+    statistics from the SpMM epilogue); returns the number of blocks written (0 without `partial`)."""
     lib = _lib.load()
     n_rows, h = y.shape
+    nblk = C.c_int(0)
     check(lib.glass_spmm_csr(_p(rowptr), _p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows,
-                             x.shape[0], h, _stream()), "spmm_csr")
+                             x.shape[0], h, _p(partial), 0 if partial is None else partial.stride(0),
+                             C.byref(nblk), _stream()), "spmm_csr")
     _count(1)
+    return nblk.value
 
 
-_define("spmm_csr_(Tensor rowptr, Tensor col, Tensor val, Tensor x, Tensor(a!) y) -> ()", _spmm_csr_)
+_define("spmm_csr_(Tensor rowptr, Tensor col, Tensor val, Tensor x, Tensor(a!) y, Tensor(b!)? partial) -> int",
+        _spmm_csr_)
 
 
-def _spmm_csr_planned_(col, val, x, y, item_begin, item_end, item_dst, long_row, long_slot, long_cnt, scratch):
+def _spmm_csr_planned_(col, val, x, y, item_begin, item_end, item_dst, long_row, long_slot, long_cnt, scratch,
+                       partial):
     lib = _lib.load()
     n_rows, h = y.shape
+    nblk = C.c_int(0)
     check(lib.glass_spmm_csr_planned(_p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows, x.shape[0], h,
                                      _p(item_begin), _p(item_end), _p(item_dst), item_begin.numel(), _p(long_row),
-                                     _p(long_slot), _p(long_cnt), long_row.numel(), _p(scratch), _stream()),
+                                     _p(long_slot), _p(long_cnt), long_row.numel(), _p(scratch), _p(partial),
+                                     0 if partial is None else partial.stride(0), C.byref(nblk), _stream()),
           "spmm_csr_planned")
     _count(2)
+    return nblk.value
 
 
 _define("spmm_csr_planned_(Tensor col, Tensor val, Tensor x, Tensor(a!) y, Tensor item_begin, Tensor item_end, "
-        "Tensor item_dst, Tensor long_row, Tensor long_slot, Tensor long_cnt, Tensor(b!) scratch) -> ()",
-        _spmm_csr_planned_)
+        "Tensor item_dst, Tensor long_row, Tensor long_slot, Tensor long_cnt, Tensor(b!) scratch, "
+        "Tensor(c!)? partial) -> int", _spmm_csr_planned_)
 
 
 def _pair_fwd_(a1, a2, w0, b0, w1, b1, mask, z_ratio, act, path, out, acts):
@@ -150,32 +160,119 @@ _define("pair_linear_mix_bwd_(Tensor dout, Tensor? acts, Tensor a1, Tensor? a2, 
         "Tensor(e!) dw1, Tensor(f!) db1, Tensor(g!) workspace) -> ()", _pair_bwd_)
 
 
-def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, drop_p, rng, out, stats, workspace):
+def _norm_operand(stats, bits, p, act):
+    """ctypes view of a row operand that the GEMM loader normalises on the fly (None: plain operand)."""
+    if stats is None:
+        return None
+    return C.byref(_lib.NormOperand(stats.data_ptr(), 0 if bits is None else bits.data_ptr(), float(p), int(act)))
+
+
+def _pair_fwd_ex_(a1, a2, w0, b0, w1, b1, mask, z_ratio, act, path, out, acts, stats1, bits1, p1, act1, stats2, bits2,
+                  p2, act2):
+    lib = _lib.load()
+    n, k1 = a1.shape
+    k2 = 0 if a2 is None else a2.shape[1]
+    h = w0.shape[0]
+    check(lib.glass_pair_linear_mix_fwd_ex(_p(a1), a1.stride(0), k1, _p(a2), 0 if a2 is None else a2.stride(0), k2,
+                                           _p(w0), _p(b0), _p(w1), _p(b1), _p(mask), z_ratio, act, _p(out),
+                                           out.stride(0), _p(acts), n, h, path, _norm_operand(stats1, bits1, p1, act1),
+                                           _norm_operand(stats2, bits2, p2, act2), _stream()), "pair_linear_mix_fwd_ex")
+    _count(1)
+
+
+_define("pair_linear_mix_fwd_ex_(Tensor a1, Tensor? a2, Tensor w0, Tensor b0, Tensor w1, Tensor b1, Tensor mask, "
+        "float z_ratio, int act, int path, Tensor(a!) out, Tensor(b!)? acts, Tensor? stats1, Tensor? bits1, float p1, "
+        "int act1, Tensor? stats2, Tensor? bits2, float p2, int act2) -> ()", _pair_fwd_ex_)
+
+
+def _pair_bwd_ex_(dout, acts, a1, a2, w0, w1, mask, z_ratio, act, path, da1, da2, dw0, db0, dw1, db1, workspace,
+                  stats1, bits1, p1, act1, stats2, bits2, p2, act2, acc1, acc2):
+    lib = _lib.load()
+    n, k1 = a1.shape
+    k2 = 0 if a2 is None else a2.shape[1]
+    h = w0.shape[0]
+    check(lib.glass_pair_linear_mix_bwd_ex(
+        _p(dout), dout.stride(0), _p(acts), _p(a1), a1.stride(0), k1, _p(a2), 0 if a2 is None else a2.stride(0), k2,
+        _p(w0), _p(w1), _p(mask), z_ratio, act, _p(da1), 0 if da1 is None else da1.stride(0), _p(da2),
+        0 if da2 is None else da2.stride(0), _p(dw0), _p(db0), _p(dw1), _p(db1), n, h, _p(workspace),
+        workspace.numel(), path, _norm_operand(stats1, bits1, p1, act1), _norm_operand(stats2, bits2, p2, act2),
+        int(acc1), int(acc2), _stream()), "pair_linear_mix_bwd_ex")
+    _count(3 if (da1 is not None or da2 is not None) else 2)
+
+
+_define("pair_linear_mix_bwd_ex_(Tensor dout, Tensor? acts, Tensor a1, Tensor? a2, Tensor w0, Tensor w1, Tensor mask, "
+        "float z_ratio, int act, int path, Tensor(a!)? da1, Tensor(b!)? da2, Tensor(c!) dw0, Tensor(d!) db0, "
+        "Tensor(e!) dw1, Tensor(f!) db1, Tensor(g!) workspace, Tensor? stats1, Tensor? bits1, float p1, int act1, "
+        "Tensor? stats2, Tensor? bits2, float p2, int act2, int acc1, int acc2) -> ()", _pair_bwd_ex_)
+
+
+def _gn_fwd_(x, weight, bias, mean_scale, eps, act, keep, drop_p, rng, bits, out, stats, workspace):
     lib = _lib.load()
     n, c = x.shape
     check(lib.glass_graphnorm_fwd(_p(x), x.stride(0), _p(weight), _p(bias), _p(mean_scale), eps, act, _p(keep),
-                                  drop_p, _p(rng), _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
+                                  drop_p, _p(rng), _p(bits), _p(out), out.stride(0), _p(stats), n, c, _p(workspace),
                                   workspace.numel(), _stream()), "graphnorm_fwd")
     _count(lib.glass_graphnorm_launches(n, c))
 
 
 _define("graphnorm_fwd_(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, int act, Tensor? keep, "
-        "float drop_p, Tensor(d!)? rng, Tensor(a!) out, Tensor(b!) stats, Tensor(c!) workspace) -> ()", _gn_fwd_)
+        "float drop_p, Tensor(d!)? rng, Tensor(e!)? bits, Tensor(a!) out, Tensor(b!) stats, Tensor(c!) workspace) -> ()",
+        _gn_fwd_)
 
 
-def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, dx, dweight, dbias, dmean_scale, workspace):
+def _gn_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, bits, dx, dweight, dbias, dmean_scale,
+             workspace):
     lib = _lib.load()
     n, c = x.shape
     check(lib.glass_graphnorm_bwd(_p(dout), dout.stride(0), _p(x), x.stride(0), _p(weight), _p(mean_scale),
-                                  _p(stats), act, _p(keep), drop_p, _p(rng), _p(dx), dx.stride(0), _p(dweight),
-                                  _p(dbias), _p(dmean_scale), n, c, _p(workspace), workspace.numel(), _stream()),
-          "graphnorm_bwd")
+                                  _p(stats), act, _p(keep), drop_p, _p(rng), _p(bits), _p(dx), dx.stride(0),
+                                  _p(dweight), _p(dbias), _p(dmean_scale), n, c, _p(workspace), workspace.numel(),
+                                  _stream()), "graphnorm_bwd")
     _count(lib.glass_graphnorm_launches(n, c))
 
 
 _define("graphnorm_bwd_(Tensor dout, Tensor x, Tensor weight, Tensor mean_scale, Tensor stats, int act, Tensor? keep, "
-        "float drop_p, Tensor? rng, Tensor(a!) dx, Tensor(b!) dweight, Tensor(c!) dbias, Tensor(d!) dmean_scale, "
-        "Tensor(e!) workspace) -> ()", _gn_bwd_)
+        "float drop_p, Tensor? rng, Tensor? bits, Tensor(a!) dx, Tensor(b!) dweight, Tensor(c!) dbias, "
+        "Tensor(d!) dmean_scale, Tensor(e!) workspace) -> ()", _gn_bwd_)
+
+
+def _gn_stats_(partial, nblk, n, weight, bias, mean_scale, eps, keep, drop_p, rng, bits, stats):
+    lib = _lib.load()
+    c = weight.numel()
+    check(lib.glass_graphnorm_stats(_p(partial), nblk, partial.stride(0), _p(weight), _p(bias), _p(mean_scale), eps,
+                                    _p(keep), drop_p, _p(rng), _p(bits), _p(stats), n, c, _stream()), "graphnorm_stats")
+    _count(1)
+
+
+_define("graphnorm_stats_(Tensor partial, int nblk, int n, Tensor weight, Tensor bias, Tensor mean_scale, float eps, "
+        "Tensor? keep, float drop_p, Tensor(c!)? rng, Tensor(b!)? bits, Tensor(a!) stats) -> ()", _gn_stats_)
+
+
+def _gn_apply_(x, stats, act, keep, drop_p, bits, out):
+    lib = _lib.load()
+    n, c = x.shape
+    check(lib.glass_graphnorm_apply(_p(x), x.stride(0), _p(stats), act, _p(keep), drop_p, _p(bits), _p(out),
+                                    out.stride(0), n, c, _stream()), "graphnorm_apply")
+    _count(1)
+
+
+_define("graphnorm_apply_(Tensor x, Tensor stats, int act, Tensor? keep, float drop_p, Tensor? bits, Tensor(a!) out) -> ()",
+        _gn_apply_)
+
+
+def _gn_bwd_from_sums_(partial, nblk, u, x, weight, mean_scale, stats, dx, dweight, dbias, dmean_scale, workspace):
+    lib = _lib.load()
+    n, c = x.shape
+    check(lib.glass_graphnorm_bwd_from_sums(_p(partial), nblk, partial.stride(0), _p(u), u.stride(0), _p(x),
+                                            x.stride(0), _p(weight), _p(mean_scale), _p(stats), _p(dx), dx.stride(0),
+                                            _p(dweight), _p(dbias), _p(dmean_scale), n, c, _p(workspace),
+                                            workspace.numel(), _stream()), "graphnorm_bwd_from_sums")
+    _count(2)
+
+
+_define("graphnorm_bwd_from_sums_(Tensor partial, int nblk, Tensor u, Tensor x, Tensor weight, Tensor mean_scale, "
+        "Tensor stats, Tensor(a!) dx, Tensor(b!) dweight, Tensor(c!) dbias, Tensor(d!) dmean_scale, "
+        "Tensor(e!) workspace) -> ()", _gn_bwd_from_sums_)
 
 
 def _emb_fwd_(table, ids, out):
@@ -389,13 +486,17 @@ def build_csr(edge_index: torch.Tensor, edge_weight: torch.Tensor, n_node: int, 
 # ---------------------------------------------------------------------------------------------
 # autograd building blocks
 # ---------------------------------------------------------------------------------------------
-def _run_spmm(rowptr, col, val, plan, x, y):
+def _run_spmm(rowptr, col, val, plan, x, y, partial=None) -> int:
     if plan is None:
-        _ops.spmm_csr_(rowptr, col, val, x, y)
-    else:
-        scratch = torch.empty((plan.n_slots, y.shape[1]), dtype=torch.float32, device=y.device)
-        _ops.spmm_csr_planned_(col, val, x, y, plan.item_begin, plan.item_end, plan.item_dst, plan.long_row,
-                               plan.long_slot, plan.long_cnt, scratch)
+        return _ops.spmm_csr_(rowptr, col, val, x, y, partial)
+    scratch = torch.empty((plan.n_slots, y.shape[1]), dtype=torch.float32, device=y.device)
+    return _ops.spmm_csr_planned_(col, val, x, y, plan.item_begin, plan.item_end, plan.item_dst, plan.long_row,
+                                  plan.long_slot, plan.long_cnt, scratch, partial)
+
+
+def _stats_table(c: int, device) -> torch.Tensor:
+    """fp64 [2*c, ld] table for per-CTA partial column sums produced by a kernel epilogue."""
+    return torch.empty((2 * c, _lib.load().glass_spmm_stats_ld()), dtype=torch.float64, device=device)
 
 
 class _SpMM(torch.autograd.Function):
@@ -501,23 +602,49 @@ _rng_states = {}
 def manual_seed(seed: int) -> None:
     """Re-seed the in-kernel dropout generator of every device (counter back to 0)."""
     for t in _rng_states.values():
-        t.copy_(torch.tensor([seed & ((1 << 63) - 1), 0], dtype=torch.int64))
+        t.copy_(torch.tensor([seed & ((1 << 63) - 1), 0, 0, 0], dtype=torch.int64))
 
 
 def _rng_state(device) -> torch.Tensor:
-    """{seed, call counter} of the dropout generator on `device`.  The seed is torch's current initial seed
+    """{seed, call counter, ticket, pad} of the dropout generator on `device`.  The seed is torch's current initial seed
     (read, not drawn: torch's own random stream -- and with it the reference-identical DataLoader shuffles --
     is left untouched), so torch.manual_seed(...) before the first training step makes runs repeatable."""
     key = (device.type, device.index)
     t = _rng_states.get(key)
     if t is None:
         seed = int(torch.initial_seed()) & ((1 << 63) - 1)
-        t = _rng_states[key] = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        t = _rng_states[key] = torch.tensor([seed, 0, 0, 0], dtype=torch.int64, device=device)
     return t
 
 
 def _gn_workspace(n, c, device):
     return torch.empty(_lib.load().glass_graphnorm_workspace_bytes(n, c), dtype=torch.uint8, device=device)
+
+
+def pack_keep_bits(keep: torch.Tensor) -> torch.Tensor:
+    """uint8 keep mask [n, c] -> packed int32 words, bit (r*c + col) % 32 of word (r*c + col) // 32 (the layout the
+    finalize kernel draws and every fused consumer reads)."""
+    flat = keep.reshape(-1).to(torch.int64)
+    pad = (-flat.numel()) % 32
+    if pad:
+        flat = torch.cat((flat, flat.new_zeros(pad)))
+    w = (flat.view(-1, 32) << torch.arange(32, device=flat.device, dtype=torch.int64)).sum(dim=1)
+    return ((w + (1 << 31)) % (1 << 32) - (1 << 31)).to(torch.int32)
+
+
+def _dropout_source(n: int, c: int, p: float, training: bool, device):
+    """(drop_p, keep, rng, bits) for one dropout site.  Generator mode: `bits` is an empty buffer that the
+    finalize kernel fills with this call's keep bits.  Injected masks (tests): the explicit uint8 mask for the
+    GraphNorm kernels plus its packed form for the fused consumers."""
+    if not training or p <= 0.0:
+        return 0.0, None, None, None
+    if p >= 1.0:
+        raise RuntimeError("dropout p must be < 1")
+    keep = _injected_keep(n, c)
+    if keep is not None:
+        return float(p), keep, None, pack_keep_bits(keep)
+    words = _lib.load().glass_dropout_bits_bytes(n, c) // 4
+    return float(p), None, _rng_state(device), torch.empty(words, dtype=torch.int32, device=device)
 
 
 class _GraphNorm(torch.autograd.Function):
@@ -527,30 +654,24 @@ class _GraphNorm(torch.autograd.Function):
         weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
         mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
         n, c = x.shape
-        keep, rng, drop_p = None, None, 0.0
-        if training and p > 0.0:
-            if p >= 1.0:
-                raise RuntimeError("dropout p must be < 1")
-            drop_p = float(p)
-            keep = _injected_keep(n, c)
-            rng = None if keep is not None else _rng_state(x.device)
+        drop_p, keep, rng, bits = _dropout_source(n, c, p, training, x.device)
         out = torch.empty((n, c), dtype=torch.float32, device=x.device)
         stats = torch.empty((6, c), dtype=torch.float32, device=x.device)
-        _ops.graphnorm_fwd_(x, weight, bias, mean_scale, float(eps), act, keep, drop_p, rng, out, stats,
+        _ops.graphnorm_fwd_(x, weight, bias, mean_scale, float(eps), act, keep, drop_p, rng, bits, out, stats,
                             _gn_workspace(n, c, x.device))
-        ctx.save_for_backward(x, weight, mean_scale, stats, keep, rng)
+        ctx.save_for_backward(x, weight, mean_scale, stats, keep, rng, bits)
         ctx.cfg = (act, drop_p)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, mean_scale, stats, keep, rng = ctx.saved_tensors
+        x, weight, mean_scale, stats, keep, rng, bits = ctx.saved_tensors
         act, drop_p = ctx.cfg
         dout, _ = _rowmajor(dout)
         n, c = x.shape
         dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
         dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
-        _ops.graphnorm_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, dx, dw, db, da,
+        _ops.graphnorm_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, bits, dx, dw, db, da,
                             _gn_workspace(n, c, x.device))
         return dx, dw, db, da, None, None, None, None
 
@@ -581,7 +702,8 @@ class _GraphNormCat(torch.autograd.Function):
         for t, w in zip(xs, widths):
             st = torch.empty((6, w), dtype=torch.float32, device=t.device)
             _ops.graphnorm_fwd_(t, weight[off:off + w], bias[off:off + w], mean_scale[off:off + w], float(eps),
-                                ACT_NONE, None, 0.0, None, out[:, off:off + w], st, _gn_workspace(n, w, t.device))
+                                ACT_NONE, None, 0.0, None, None, out[:, off:off + w], st,
+                                _gn_workspace(n, w, t.device))
             stats.append(st)
             off += w
         ctx.save_for_backward(weight, mean_scale, *xs, *stats)
@@ -601,7 +723,7 @@ class _GraphNormCat(torch.autograd.Function):
         for t, st, w in zip(xs, stats, widths):
             dx = torch.empty((n, w), dtype=torch.float32, device=t.device)
             _ops.graphnorm_bwd_(dout[:, off:off + w], t, weight[off:off + w], mean_scale[off:off + w], st, ACT_NONE,
-                                None, 0.0, None, dx, dw[off:off + w], db[off:off + w], da[off:off + w],
+                                None, 0.0, None, None, dx, dw[off:off + w], db[off:off + w], da[off:off + w],
                                 _gn_workspace(n, w, t.device))
             dxs.append(dx)
             off += w
@@ -630,6 +752,151 @@ def _validate_ids(ids: torch.Tensor, rows: int, what: str) -> None:
     if len(_ids_checked) > 64:
         _ids_checked.clear()
     _ids_checked[key] = True
+
+
+class _SpMMGraphNorm(torch.autograd.Function):
+    """dropout(act(GraphNorm(adj @ x))) (impl/models.py:164-166) with the column statistics taken in the SpMM
+    epilogue: no separate pass over `adj @ x` to find its mean / variance."""
+
+    @staticmethod
+    def forward(ctx, x, adj: CSRAdj, weight, bias, mean_scale, eps, act, p, training):
+        x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
+        if x.shape[0] != adj.n:
+            raise RuntimeError(f"spmm: x has {x.shape[0]} rows but the adjacency is {adj.n} x {adj.n}")
+        weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
+        mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
+        n, c = adj.n, x.shape[1]
+        y = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        partial = _stats_table(c, x.device)
+        nblk = _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, x, y, partial)
+        drop_p, keep, rng, bits = _dropout_source(n, c, p, training, x.device)
+        stats = torch.empty((6, c), dtype=torch.float32, device=x.device)
+        _ops.graphnorm_stats_(partial, nblk, n, weight, bias, mean_scale, float(eps), keep, drop_p, rng, bits, stats)
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        _ops.graphnorm_apply_(y, stats, act, keep, drop_p, bits, out)
+        ctx.save_for_backward(y, weight, mean_scale, stats, keep, rng, bits)
+        ctx.adj, ctx.cfg = adj, (act, drop_p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, weight, mean_scale, stats, keep, rng, bits = ctx.saved_tensors
+        act, drop_p = ctx.cfg
+        adj = ctx.adj
+        dout, _ = _rowmajor(dout)
+        n, c = y.shape
+        dy = torch.empty((n, c), dtype=torch.float32, device=y.device)
+        dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
+        _ops.graphnorm_bwd_(dout, y, weight, mean_scale, stats, act, keep, drop_p, rng, bits, dy, dw, db, da,
+                            _gn_workspace(n, c, y.device))
+        gx = torch.empty_like(dy)
+        _run_spmm(adj.rowptr_t, adj.col_t, adj.val_t, adj.plan_t, dy, gx)
+        return gx, None, dw, db, da, None, None, None, None
+
+
+def spmm_graph_norm(adj: CSRAdj, x, weight, bias, mean_scale, eps: float = 1e-5, act: int = ACT_NONE, p: float = 0.0,
+                    training: bool = False):
+    if adj.n == 0 or x.shape[0] == 0:
+        return graph_norm(spmm(adj, x), weight, bias, mean_scale, eps, act, p, training)
+    return _SpMMGraphNorm.apply(x, adj, weight, bias, mean_scale, eps, act, p, training)
+
+
+def conv_fusable(k_in: int, h: int, path: Optional[int] = None) -> bool:
+    """True when one GLASSConv layer (in width k_in, out width h) can run as the fused chain below: the
+    tcgen05 kernels with operands normalised on load (glass_pair_norm_operand_supported)."""
+    path = _gemm_path if path is None else path
+    if path == GEMM_SIMT:
+        return False
+    lib = _lib.load()
+    return bool(lib.glass_pair_norm_operand_supported(k_in, 0, h)) and bool(lib.glass_pair_norm_operand_supported(h, k_in, h))
+
+
+class _GlassConv(torch.autograd.Function):
+    """One GLASSConv layer (impl/models.py:153-174) as FOUR kernels forward:
+        pair GEMM (trans_fns + activation + label mix)                                         :158-162
+        SpMM whose epilogue also emits the GraphNorm column sums                               :164-165
+        finalize (normalisation constants + this call's dropout bits)
+        pair GEMM over the virtual concat [dropout(GraphNorm(adj @ x)) | x_] whose loader applies the norm
+        and the keep bits to the first operand on the fly (neither the normalised matrix nor the concat
+        exists in memory)                                                                      :165-173
+    and backward: comb dX / dW (the dW loader re-creates the normalised operand), GraphNorm backward, A^T SpMM,
+    trans dX (ACCUMULATING into the gradient of x_, which fed both GEMMs) / dW."""
+
+    @staticmethod
+    def forward(ctx, x_, adj, tw0, tb0, tw1, tb1, gw, gb, gms, cw0, cb0, cw1, cb1, mask, z_ratio, act, eps, p,
+                training, path):
+        x_, _ = _rowmajor(_req(x_, torch.float32, "x_", 2))
+        mask = _req(mask, torch.uint8, "mask", 1)
+        n, k_in = x_.shape
+        h = tw0.shape[0]
+        dev = x_.device
+        if n != adj.n or mask.shape[0] != n:
+            raise RuntimeError(f"GLASSConv: x_ has {n} rows, adjacency {adj.n}, mask {mask.shape[0]}")
+        f32 = dict(dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad)
+        # :158-162
+        xm = torch.empty((n, h), **f32)
+        acts = torch.empty((n, 2 * h), **f32) if (need_grad and act != ACT_NONE) else None
+        _ops.pair_linear_mix_fwd_(x_, None, tw0, tb0, tw1, tb1, mask, float(z_ratio), act, path, xm, acts)
+        # :164 with the statistics of :165
+        y = torch.empty((n, h), **f32)
+        partial = _stats_table(h, dev)
+        nblk = _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, xm, y, partial)
+        drop_p, keep, rng, bits = _dropout_source(n, h, p, training, dev)
+        stats = torch.empty((6, h), **f32)
+        _ops.graphnorm_stats_(partial, nblk, n, gw, gb, gms, float(eps), keep, drop_p, rng, bits, stats)
+        # :165-173
+        out = torch.empty((n, h), **f32)
+        _ops.pair_linear_mix_fwd_ex_(y, x_, cw0, cb0, cw1, cb1, mask, float(z_ratio), ACT_NONE, path, out, None,
+                                     stats, bits, drop_p, ACT_NONE, None, None, 0.0, ACT_NONE)
+        ctx.save_for_backward(x_, acts, y, stats, keep, rng, bits, mask, tw0, tw1, gw, gms, cw0, cw1)
+        ctx.adj, ctx.cfg = adj, (float(z_ratio), act, drop_p, path)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_, acts, y, stats, keep, rng, bits, mask, tw0, tw1, gw, gms, cw0, cw1 = ctx.saved_tensors
+        z_ratio, act, drop_p, path = ctx.cfg
+        adj = ctx.adj
+        dout, _ = _rowmajor(dout)
+        n, k_in = x_.shape
+        h = tw0.shape[0]
+        dev = dout.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        want_dx = ctx.needs_input_grad[0]
+        # comb GEMM: gradient w.r.t. the normalised operand (dg) and the x_ half of the concat
+        dg = torch.empty((n, h), **f32)
+        dx_ = torch.empty((n, k_in), **f32) if want_dx else None
+        dcw0, dcw1 = torch.empty_like(cw0), torch.empty_like(cw1)
+        dcb0, dcb1 = torch.empty(h, **f32), torch.empty(h, **f32)
+        ws = torch.empty(lib.glass_pair_linear_mix_bwd_workspace_bytes(n, h, h + k_in), dtype=torch.uint8, device=dev)
+        _ops.pair_linear_mix_bwd_ex_(dout, None, y, x_, cw0, cw1, mask, z_ratio, ACT_NONE, path, dg, dx_, dcw0, dcb0,
+                                     dcw1, dcb1, ws, stats, bits, drop_p, ACT_NONE, None, None, 0.0, ACT_NONE, 0, 0)
+        # GraphNorm + dropout backward, then A^T
+        dy = torch.empty((n, h), **f32)
+        dgw, dgb, dgms = torch.empty_like(gw), torch.empty_like(gw), torch.empty_like(gw)
+        _ops.graphnorm_bwd_(dg, y, gw, gms, stats, ACT_NONE, keep, drop_p, rng, bits, dy, dgw, dgb, dgms,
+                            _gn_workspace(n, h, dev))
+        dxm = dg                                                   # dg is dead: reuse its storage
+        _run_spmm(adj.rowptr_t, adj.col_t, adj.val_t, adj.plan_t, dy, dxm)
+        # trans GEMM: its dX is ADDED to the x_ gradient the comb GEMM wrote above
+        dtw0, dtw1 = torch.empty_like(tw0), torch.empty_like(tw1)
+        dtb0, dtb1 = torch.empty(h, **f32), torch.empty(h, **f32)
+        ws = torch.empty(lib.glass_pair_linear_mix_bwd_workspace_bytes(n, h, k_in), dtype=torch.uint8, device=dev)
+        _ops.pair_linear_mix_bwd_ex_(dxm, acts, x_, None, tw0, tw1, mask, z_ratio, act, path, dx_, None, dtw0, dtb0,
+                                     dtw1, dtb1, ws, None, None, 0.0, ACT_NONE, None, None, 0.0, ACT_NONE,
+                                     1 if want_dx else 0, 0)
+        return (dx_, None, dtw0, dtb0, dtw1, dtb1, dgw, dgb, dgms, dcw0, dcb0, dcw1, dcb1, None, None, None, None,
+                None, None, None)
+
+
+def glass_conv(x_, adj: CSRAdj, trans, gn, comb, mask, z_ratio: float, act: int, p: float, training: bool,
+               path: Optional[int] = None):
+    """Fused GLASSConv.forward; trans / comb = (w0, b0, w1, b1), gn = (weight, bias, mean_scale, eps)."""
+    gw, gb, gms, eps = gn
+    return _GlassConv.apply(x_, adj, *trans, gw, gb, gms, *comb, mask, z_ratio, act, eps, p, training,
+                            _gemm_path if path is None else path)
 
 
 class _Embedding(torch.autograd.Function):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLASS_B200_ABI_VERSION 1
+#define GLASS_B200_ABI_VERSION 2
 
 typedef enum {
     GLASS_OK = 0,
@@ -75,9 +75,17 @@ int glass_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t
  * order, bit-equal to a sequential CPU loop.  Smaller graphs: 32/G neighbour slots per row (G = h/4
  * feature lanes), slot s adds every (32/G)-th entry, the slot sums are added by a fixed butterfly.
  * n_rows = rows of the CSR block; n_cols = rows of x (every column index must be < n_cols).
+ * Fused GraphNorm statistics (impl/models.py:164-165): with stats_partial != NULL the epilogue also emits, per
+ * CTA, the fp64 column sums of y and y^2 -- stats_partial[(which*h + c)*stats_ld + blk], blk < *stats_nblk_host
+ * (written on the host before the call returns; stats_ld >= glass_spmm_stats_ld() always suffices) -- which
+ * glass_graphnorm_stats turns into the normalisation constants without another pass over y.
  * ------------------------------------------------------------------------------------------ */
+int glass_spmm_stats_ld(void);
+/* Run-time tuning knobs for benchmark scripts ("spmm_variant", "spmm_waves"); the defaults are the measured best. */
+int glass_tune(const char* name, int value);
 int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, const float* x,
-                   int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h, void* stream);
+                   int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h,
+                   double* stats_partial, int stats_ld, int* stats_nblk_host, void* stream);
 
 /* Skewed (power-law) graphs: rows longer than max_len entries are split into several work items whose
  * partial sums go to a scratch matrix [n_slots, h] and are added up in chunk order (deterministic).
@@ -94,7 +102,8 @@ int glass_spmm_csr_planned(const int32_t* col, const float* val, const float* x,
                            int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const int32_t* item_begin,
                            const int32_t* item_end, const int32_t* item_dst, int64_t n_items,
                            const int32_t* long_row, const int32_t* long_slot, const int32_t* long_cnt,
-                           int64_t n_long, float* scratch, void* stream);
+                           int64_t n_long, float* scratch, double* stats_partial, int stats_ld,
+                           int* stats_nblk_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Label-mixed pair of Linear layers  (impl/models.py:158-162 with activation, :169-173 without)
@@ -110,6 +119,25 @@ int glass_pair_linear_mix_fwd(const float* a1, int64_t lda1, int k1, const float
                               const uint8_t* mask, float z_ratio, int act, float* out, int64_t ldo,
                               float* acts, int64_t n, int h, int path, void* stream);
 
+/* The same with operands that are NORMALISED WHILE THEY ARE LOADED (north star: "fused with the label mix,
+ * GraphNorm and the concat", impl/models.py:165-167 and :249-251): for an operand with a statistics table,
+ *   a[r, c] <- keep/(1-p) * act(scale[c]*(a[r, c] - am[c]) + bias[c])
+ * with rows 0, 1, 4 of the stats [6, k] table of glass_graphnorm_* and the packed keep bits of that call, so the
+ * GraphNorm output / dropout / concat never exist in memory.  n1 / n2 may be NULL (plain operand).  Needs the
+ * tcgen05 kernels: h in {64, 128}, k1 and k2 multiples of 32, k1+k2 <= 128 (glass_pair_norm_operand_supported). */
+typedef struct {
+    const float* stats;     /* device [6, k] (NULL: operand used as is) */
+    const uint32_t* bits;   /* device packed keep bits, bit r*k + c (NULL: no dropout) */
+    float drop_p;           /* probability the bits were drawn with (0: none) */
+    int act;                /* glass_act applied between the norm and the dropout */
+} glass_norm_operand;
+int glass_pair_norm_operand_supported(int k1, int k2, int h);
+int glass_pair_linear_mix_fwd_ex(const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2, int k2,
+                                 const float* w0, const float* b0, const float* w1, const float* b1,
+                                 const uint8_t* mask, float z_ratio, int act, float* out, int64_t ldo,
+                                 float* acts, int64_t n, int h, int path, const glass_norm_operand* n1,
+                                 const glass_norm_operand* n2, void* stream);
+
 /* Backward of the above.  dout [n,h]; acts as saved by fwd (NULL iff act == NONE).
  * da1 [n,k1], da2 [n,k2] (either may be NULL to skip), dw0,dw1 [h,k1+k2], db0,db1 [h].
  * workspace: glass_pair_linear_mix_bwd_workspace_bytes(n, h, k1+k2) bytes (split-N partials,
@@ -121,6 +149,17 @@ int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts
                               float* da1, int64_t ldda1, float* da2, int64_t ldda2, float* dw0, float* db0,
                               float* dw1, float* db1, int64_t n, int h, void* workspace,
                               size_t workspace_bytes, int path, void* stream);
+/* ..._ex: n1 / n2 as in fwd_ex (the dW kernel re-creates the normalised operand on load; da1 / da2 are the
+ * gradients with respect to the NORMALISED operands); accumulate_da1 / accumulate_da2 != 0 add to da1 / da2
+ * instead of overwriting them (an operand that fed two GEMMs, e.g. x_ of impl/models.py:158 and :167). */
+int glass_pair_linear_mix_bwd_ex(const float* dout, int64_t lddo, const float* acts, const float* a1,
+                                 int64_t lda1, int k1, const float* a2, int64_t lda2, int k2,
+                                 const float* w0, const float* w1, const uint8_t* mask, float z_ratio, int act,
+                                 float* da1, int64_t ldda1, float* da2, int64_t ldda2, float* dw0, float* db0,
+                                 float* dw1, float* db1, int64_t n, int h, void* workspace,
+                                 size_t workspace_bytes, int path, const glass_norm_operand* n1,
+                                 const glass_norm_operand* n2, int accumulate_da1, int accumulate_da2,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GraphNorm over the whole graph (PyG GraphNorm with batch=None; call sites impl/models.py:165,
@@ -129,28 +168,56 @@ int glass_pair_linear_mix_bwd(const float* dout, int64_t lddo, const float* acts
  *   mu = mean_rows(x); o = x - mean_scale*mu; var = mean_rows(o^2); rstd = 1/sqrt(var+eps)
  *   out = keep/(1-p) * act(weight*o*rstd + bias)
  * stats [6, c]: rows = scale (weight*rstd), am (mean_scale*mu), mu, rstd, bias, dropout call id -- written
- * by fwd, consumed by bwd.  Dropout (drop_p > 0): `keep` uint8 [n,c] (ld c) is an explicit mask; with
- * keep == NULL and rng != NULL the kernels generate the bits themselves (Philox4x32-10 keyed by rng[0],
- * counter = element index and a per-call id taken from rng[1], which fwd increments) and bwd regenerates
- * them from the id saved in `stats`; with both NULL there is no dropout.
+ * by fwd, consumed by bwd and by every fused consumer.
+ * Dropout (drop_p > 0), three sources of the keep decision:
+ *   keep uint8 [n,c] (ld c)  explicit mask (tests inject one to compare train-mode passes with the oracle);
+ *   rng + bits               rng = {seed, call counter, ticket} (3 x uint64, device); the finalize kernel draws
+ *                            this call's keep bits ONCE (Philox4x32-10, counter = element index / 4 and the call
+ *                            id) into `bits` (glass_dropout_bits_bytes(n, c) bytes, bit r*c+col of a row-major
+ *                            bit string, 1 = keep) and advances the counter; apply, backward and the operand
+ *                            loaders of the pair GEMM read one bit per element;
+ *   rng alone                the same bits regenerated inside every kernel (no buffer; the one-launch cluster
+ *                            kernel for matrices of at most 48 K elements always works this way).
  * Column sums are accumulated in fp64 per block and reduced in block order (deterministic).
  * workspace: glass_graphnorm_workspace_bytes(n, c).
  * Matrices of at most 48 K elements (c <= 256) run as ONE launch on a thread-block cluster (partials
- * exchanged through distributed shared memory); larger ones as three (sums, finalise, element-wise).
+ * exchanged through distributed shared memory); larger ones as three (sums, finalise + bits, element-wise).
  * glass_graphnorm_launches(n, c) tells which (1 or 3; pure host arithmetic, for launch accounting).
  * ------------------------------------------------------------------------------------------ */
 size_t glass_graphnorm_workspace_bytes(int64_t n, int c);
+size_t glass_dropout_bits_bytes(int64_t n, int c);
 int glass_graphnorm_launches(int64_t n, int c);
 int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* weight, const float* bias,
                         const float* mean_scale, float eps, int act, const uint8_t* keep, float drop_p,
-                        unsigned long long* rng, float* out, int64_t ldo, float* stats, int64_t n, int c,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        unsigned long long* rng, uint32_t* bits, float* out, int64_t ldo, float* stats,
+                        int64_t n, int c, void* workspace, size_t workspace_bytes, void* stream);
 /* dx [n,c]; dweight, dbias, dmean_scale [c] are OVERWRITTEN (not accumulated). */
 int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* weight,
                         const float* mean_scale, const float* stats, int act, const uint8_t* keep,
-                        float drop_p, const unsigned long long* rng, float* dx, int64_t lddx, float* dweight, float* dbias,
-                        float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        float drop_p, const unsigned long long* rng, const uint32_t* bits, float* dx,
+                        int64_t lddx, float* dweight, float* dbias, float* dmean_scale, int64_t n, int c,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused forms (north star: "adj@x fused with the label mix, GraphNorm and the concat", impl/models.py:164-167).
+ * The column sums come out of the kernel that PRODUCES x (glass_spmm_csr_stats, the *_ex pair GEMM) as fp64
+ * partials partial[(which*c + col)*ldp + blk], which = 0: sum x, 1: sum x^2, blk < nblk.
+ *   glass_graphnorm_stats      partials -> stats (+ this call's dropout bits); ONE small launch
+ *   glass_graphnorm_apply      out = keep/(1-p) * act(scale*(x-am)+bias) from stats (when x must be materialised)
+ *   glass_graphnorm_bwd_from_sums  backward when the producer of the gradient already wrote
+ *                              u = dout*keep/(1-p)*act'(pre) and the partials of S1 = sum u, S2 = sum u*yhat
+ *                              (dX epilogue of glass_pair_linear_mix_bwd_ex): finalise + dx = a*u + b*yhat + g.
+ *                              u and dx may alias.  workspace >= 3*c floats (256-byte aligned size). */
+int glass_graphnorm_stats(const double* partial, int nblk, int ldp, const float* weight, const float* bias,
+                          const float* mean_scale, float eps, const uint8_t* keep, float drop_p,
+                          unsigned long long* rng, uint32_t* bits, float* stats, int64_t n, int c, void* stream);
+int glass_graphnorm_apply(const float* x, int64_t ldx, const float* stats, int act, const uint8_t* keep,
+                          float drop_p, const uint32_t* bits, float* out, int64_t ldo, int64_t n, int c,
+                          void* stream);
+int glass_graphnorm_bwd_from_sums(const double* partial, int nblk, int ldp, const float* u, int64_t ldu,
+                                  const float* x, int64_t ldx, const float* weight, const float* mean_scale,
+                                  const float* stats, float* dx, int64_t lddx, float* dweight, float* dbias,
+                                  float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * nn.Embedding lookup (impl/models.py:248) and its dense gradient.

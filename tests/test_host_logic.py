@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/glass_b200.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
-    assert _lib.load().glass_abi_version() == 1
+    assert _lib.load().glass_abi_version() == 2
     # size queries are pure host arithmetic and must work without a GPU
     assert _lib.load().glass_pair_linear_mix_bwd_workspace_bytes(57333, 64, 128) > 0
     assert _lib.load().glass_graphnorm_workspace_bytes(57333, 64) > 0
