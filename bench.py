@@ -201,16 +201,21 @@ def spmm_roofline(adj, h: int, reps: int = 20):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo / (avg * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch come from an `ncu --set full` capture (profiles/); they are only reported when the
+    # capture was taken from THIS build of spmm.cu (digest of the source stamped into the file) and this graph
+    traffic, traffic_note = None, "no ncu capture for this build of csrc/spmm.cu"
     try:
+        import hashlib
+        with open(os.path.join(ROOT, "glass_b200", "csrc", "spmm.cu"), "rb") as f:
+            digest = hashlib.sha256(f.read()).hexdigest()[:16]
         with open(os.path.join(ROOT, "profiles", "spmm_traffic.json")) as f:
-            t = json.load(f)
-            if t.get("nnz") == adj.nnz and t.get("h") == h:
-                traffic = t["dram_bytes_per_launch"]
+            for t in json.load(f)["captures"]:
+                if t.get("nnz") == adj.nnz and t.get("h") == h and t.get("spmm_cu_sha16") == digest:
+                    traffic, traffic_note = t["dram_bytes_per_launch"], t.get("source", "")
     except Exception:
         pass
     return {"bound": "hbm", "kernel": "k_spmm (glass_spmm_csr)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": algo, "us_per_launch": avg * 1e3,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes": algo, "us_per_launch": avg * 1e3,
             "us_min": ms[0] * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
             "gather_bytes_l2": 4 * h * adj.nnz, "gather_gbs_l2": 4 * h * adj.nnz / (avg * 1e-3) / 1e9,
             "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0}
@@ -290,13 +295,14 @@ def run_product(args):
         line = base_line(args, wl, value, ms / args.steps)
         line["e2e"] = {"value": e2e_value, "unit": "subgraphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "api": "glass_b200.graphed.train_epoch(GraphedTrainStep, pinned host batches), loss.item() every step"}
-        line["config"]["cuda_graph"] = not args.no_graph
+        line["cuda_graph"] = not args.no_graph
         line["gpu_launches"] = launches
         line["clocks"] = clocks.summary()
         adj = model.conv.convs[0].adj
         line["roofline"] = spmm_roofline(adj, p["hidden_dim"])
-        # inference throughput of the same model / batches (impl/train.py:20-34 forward only), one graph per batch
-        from glass_b200.graphed import GraphedForward
+        # inference throughput of the same model / batches (impl/train.py:20-34 forward only): one graph per batch,
+        # and the multi-label-batch evaluator (adj @ U once per epoch + sparse label correction per batch)
+        from glass_b200.graphed import GraphedForward, GraphedSharedBaseForward
         fwd = GraphedForward(model, x, ei, ew, dev_batches[0][0])
         for pos, y in dev_batches[:args.warmup]:
             fwd(pos)
@@ -308,6 +314,33 @@ def run_product(args):
         torch.cuda.synchronize()
         line["infer"] = {"value": bs * args.steps / (e0.elapsed_time(e1) * 1e-3), "unit": "subgraphs/s",
                          "n_gpus": 1, "ms_per_step": e0.elapsed_time(e1) / args.steps}
+        try:
+            sb = GraphedSharedBaseForward(model, x, ei, ew, dev_batches[0][0])
+            per_epoch = max(1, int(wl["g"].pos.shape[0] - wl["trn_pos"].shape[0]) // bs)   # val + test batches
+            for pos, y in dev_batches[:args.warmup]:
+                sb(pos)
+            torch.cuda.synchronize()
+            e0.record()
+            for i, (pos, y) in enumerate(dev_batches[args.warmup:]):
+                if i % per_epoch == 0:
+                    sb.refresh()                    # new weights every evaluation epoch
+                sb(pos)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_sb = e0.elapsed_time(e1)
+            e0.record()
+            for pos, y in dev_batches[args.warmup:]:
+                sb(pos)
+            e1.record()
+            torch.cuda.synchronize()
+            line["infer_shared_base"] = {
+                "value": bs * args.steps / (ms_sb * 1e-3), "unit": "subgraphs/s", "ms_per_step": ms_sb / args.steps,
+                "refresh_every_batches": per_epoch, "ms_per_step_steady": e0.elapsed_time(e1) / args.steps,
+                "what": "glass_b200.graphed.GraphedSharedBaseForward: label-independent base once per evaluation epoch "
+                        "(val + test split), sparse label correction per batch; same logits as `infer`"}
+            del sb
+        except NotImplementedError as e:
+            line["infer_shared_base"] = {"unavailable": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             v, per = cpu_port_steps(wl, args.cpu_steps, 1)
             line["cpu_baseline"] = {"value": v, "unit": "subgraphs/s", "cores": torch.get_num_threads(),
@@ -315,8 +348,8 @@ def run_product(args):
                                     "sample": f"{args.cpu_steps} train steps (after 1 warm-up) of batch {bs} on the full "
                                               f"{wl['name']} graph, oracle port of impl/models.py",
                                     "ms_per_step": per * 1e3}
-        if world == 1 and args.gpu_eager_baseline:
-            v, per = cpu_port_steps(wl, 20, 3, device=dev)
+        if world == 1 and not args.no_gpu_eager_baseline:
+            v, per = cpu_port_steps(wl, 10, 2, device=dev)
             line["gpu_eager_baseline"] = {"value": v, "unit": "subgraphs/s", "ms_per_step": per * 1e3,
                                           "what": "oracle port of impl/models.py run eagerly on this GPU "
                                                   "(torch.sparse COO @ dense -> cuSPARSE, ATen element-wise, torch Adam)"}
@@ -340,7 +373,9 @@ def run_product(args):
         os._exit(0)
 
 
-OTHER_CONFIGS = ("density", "cut_ratio", "component", "ppi_bp_shaped")   # BASELINE.json configs[0..2]
+# BASELINE.json configs[0..2] + the skewed variant of configs[3] ("use a skewed /
+# power-law degree generator as well as uniform")
+OTHER_CONFIGS = ("density", "cut_ratio", "component", "ppi_bp_shaped", "em_user_shaped_powerlaw")
 
 
 def quick_config(name, dev, steps, warmup, cpu_steps):
@@ -373,7 +408,9 @@ def quick_config(name, dev, steps, warmup, cpu_steps):
     out = {"value": p["batch_size"] / (ms * 1e-3), "unit": "subgraphs/s", "ms_per_step": ms,
            "gpu_launches_per_step": launches, "nodes": int(g.x.shape[0]), "nnz": int(model.conv.convs[0].adj.nnz),
            "hidden_dim": p["hidden_dim"], "conv_layer": p["conv_layer"], "batch_size": p["batch_size"]}
-    if cpu_steps:
+    if name.startswith("em_user"):
+        out["roofline"] = spmm_roofline(model.conv.convs[0].adj, p["hidden_dim"])
+    if cpu_steps and not name.startswith("em_user"):
         v, per = cpu_port_steps(wl, cpu_steps, 1)
         out["cpu_port"] = {"value": v, "ms_per_step": per * 1e3, "cores": torch.get_num_threads()}
     return out
@@ -391,8 +428,8 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short runs of the other BASELINE.json configs (`other_configs` key)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
-    ap.add_argument("--gpu-eager-baseline", action="store_true",
-                    help="also time the reference's eager torch.sparse op sequence on this GPU (extra key)")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true",
+                    help="skip timing the reference's eager torch.sparse op sequence on this GPU (`gpu_eager_baseline` key)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "glass_spmm_plan_build": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "glass_spmm_csr_planned": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i64,
                                       _vp, _vp, _vp, _i64, _vp, _vp, _i32, C.POINTER(C.c_int), _vp]),
+    "glass_spmm_delta": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64,
+                                _vp, _vp, _vp, _i64, _vp, _vp, _i32, C.POINTER(C.c_int), _vp]),
     "glass_pair_linear_mix_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
                                          _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "glass_pair_norm_operand_supported": (_i32, [_i32, _i32, _i32]),
@@ -58,6 +60,12 @@ PROTOTYPES = {
     "glass_graphnorm_apply": (_i32, [_vp, _i64, _vp, _i32, _vp, _f32, _vp, _vp, _i64, _i64, _i32, _vp]),
     "glass_graphnorm_bwd_from_sums": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
                                              _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
+    "glass_graphnorm_partials_ld": (_i32, []),
+    "glass_graphnorm_partials": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, C.POINTER(C.c_int), _vp]),
+    "glass_graphnorm_bwd_partials": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _vp, _f32, _vp, _i64, _i32, _vp, _i32,
+                                            C.POINTER(C.c_int), _vp]),
+    "glass_graphnorm_bwd_finish": (_i32, [_vp, _i32, _i32, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _f32,
+                                          _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
     "glass_embedding_fwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "glass_embedding_bwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
     "glass_segment_pool_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _i64, _vp]),
@@ -66,6 +74,9 @@ PROTOTYPES = {
     "glass_segment_pool_batch_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "glass_adam_chunk": (_i32, []),
     "glass_adam_step": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _f32, _f32, _f32, _f32, _vp]),
+    "glass_dp_flags_bytes": (_i32, []),
+    "glass_dp_adam_step": (_i32, [_i32, _i32, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _i64, _i64, _i64, _i64,
+                                  _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "glass_maxzoz": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "glass_label_mask": (_i32, [_vp, _vp, _i64, _vp]),
     "glass_pad2batch": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -40,15 +40,35 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 
 // expm1 for v <= 0 without the slow libm path: degree-5 Taylor below 1/16 (error < 1e-9 relative),
 // MUFU-based exp elsewhere (2 ulp of exp(v), i.e. < 3e-6 relative for |v| >= 1/16).
+// The exponential is one MUFU.EX2 (ex2.approx.ftz, relative error 2^-22) issued through inline PTX: __expf adds a
+// denormal-range fix-up whose control flow made nvcc emit a divergent branch region PER ELEMENT in the GEMM
+// epilogues (ncu source view: 16 BSSY/BSYNC pairs per 8 columns, ~800 instructions per epilogue iteration).
+// For v <= 0 the result of ex2 is in (0, 1]: nothing to fix up; positive v only produces a value the caller discards.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float expm1_neg(float v) {
     const float t = v * (1.f + v * (0.5f + v * (0.16666667f + v * (0.041666668f + v * 0.0083333338f))));
-    const float e = __expf(v) - 1.f;
+    const float e = ex2_approx(v * 1.4426950408889634f) - 1.f;
     return v > -0.0625f ? t : e;
 }
 
+// ELU without a branch: nvcc turns `v > 0 ? v : expm1(v)` into a divergent branch around the exponential (one
+// BSSY/BSYNC region per element); max(v, 0) + expm1(min(v, 0)) is the same value (expm1(0) == 0 exactly) in
+// straight-line code.  The asm is volatile so that it cannot be sunk back into a conditional region.
+__device__ __forceinline__ float elu_fwd(float v) {
+    const float m = fminf(v, 0.f);
+    float e;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(m * 1.4426950408889634f));
+    const float t = m * (1.f + m * (0.5f + m * (0.16666667f + m * (0.041666668f + m * 0.0083333338f))));
+    return fmaxf(v, 0.f) + (m > -0.0625f ? t : e - 1.f);
+}
+
 __device__ __forceinline__ float act_fwd(float v, int act) {
-    if (act == GLASS_ACT_RELU) return v > 0.f ? v : 0.f;
-    if (act == GLASS_ACT_ELU) return v > 0.f ? v : expm1_neg(v);
+    if (act == GLASS_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == GLASS_ACT_ELU) return elu_fwd(v);
     return v;
 }
 // derivative expressed through the POST-activation value (ELU alpha = 1: d/dx = y + 1 for x <= 0)
@@ -61,7 +81,7 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
 // the same derivative from the PRE-activation value: exp(x) has no cancellation near 0, so no expm1 blend
 __device__ __forceinline__ float act_grad_from_pre(float v, int act) {
     if (act == GLASS_ACT_RELU) return v > 0.f ? 1.f : 0.f;
-    if (act == GLASS_ACT_ELU) return v > 0.f ? 1.f : __expf(v);
+    if (act == GLASS_ACT_ELU) return v > 0.f ? 1.f : ex2_approx(v * 1.4426950408889634f);
     return 1.f;
 }
 

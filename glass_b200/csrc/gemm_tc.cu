@@ -125,6 +125,22 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// 256-bit global stores / loads (sm_100: STG.E.ENL2.256): a lane of the epilogue owns a ROW, so every store
+// instruction touches 32 different rows; with 128-bit stores each lane writes half a 32-byte sector per instruction
+// and the SM's store path (one sector per cycle) runs at half rate -- measured 800-900 cycles for the six stores of
+// one epilogue iteration.  One 256-bit store per lane writes whole sectors.
+__device__ __forceinline__ void st_global_256(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+
 __device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
     hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
     hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -187,6 +203,7 @@ struct TcParams {
     NormOp n1, n2;       // forward: normalisation applied to a1 / a2 on load (stats == NULL: plain operand)
     int acc1, acc2;      // backward: da1 / da2 += instead of =
     int staged;          // epilogue goes through per-warp shared-memory tiles -> 64-byte row segments per store
+    int wide;            // epilogue rows are 32-byte aligned: 256-bit stores
     long long* dbg;      // optional timeline of CTA 0 (GLASS_B200_TC_TIMELINE): [0]=start [1]=setup done,
 };                       // [16+i] loader consumed K-block i, [80+i] MMA committed K-block i, [144+t] epilogue done tile t, [200]=end
 
@@ -194,7 +211,9 @@ __device__ __forceinline__ void stamp(long long* dbg, int idx) {
     if (dbg && blockIdx.x == 0) dbg[idx] = clock64();
 }
 
-template <bool BWD, bool NORM>
+// ACT is a template parameter: with a run-time activation every element of the epilogue / the dP loader carried two
+// compare-and-branch pairs (the kernels are bound by the instruction count of their CUDA-core warps, not by memory).
+template <bool BWD, bool NORM, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -326,10 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         for (int ch = 0; ch < 4; ++ch) {
                             const float4 ba = ldg_f4(P.b0 + cb + 4 * ch), bb = ldg_f4(P.b1 + cb + 4 * ch);   // 512 B, L1 resident
                             float4 q0, q1, o4;
-                            q0.x = act_fwd(p0[4 * ch] + ba.x, P.act), q0.y = act_fwd(p0[4 * ch + 1] + ba.y, P.act);
-                            q0.z = act_fwd(p0[4 * ch + 2] + ba.z, P.act), q0.w = act_fwd(p0[4 * ch + 3] + ba.w, P.act);
-                            q1.x = act_fwd(p1[4 * ch] + bb.x, P.act), q1.y = act_fwd(p1[4 * ch + 1] + bb.y, P.act);
-                            q1.z = act_fwd(p1[4 * ch + 2] + bb.z, P.act), q1.w = act_fwd(p1[4 * ch + 3] + bb.w, P.act);
+                            q0.x = act_fwd(p0[4 * ch] + ba.x, ACT), q0.y = act_fwd(p0[4 * ch + 1] + ba.y, ACT);
+                            q0.z = act_fwd(p0[4 * ch + 2] + ba.z, ACT), q0.w = act_fwd(p0[4 * ch + 3] + ba.w, ACT);
+                            q1.x = act_fwd(p1[4 * ch] + bb.x, ACT), q1.y = act_fwd(p1[4 * ch + 1] + bb.y, ACT);
+                            q1.z = act_fwd(p1[4 * ch + 2] + bb.z, ACT), q1.w = act_fwd(p1[4 * ch + 3] + bb.w, ACT);
                             o4.x = __fadd_rn(__fmul_rn(c1, q1.x), __fmul_rn(c0, q0.x));
                             o4.y = __fadd_rn(__fmul_rn(c1, q1.y), __fmul_rn(c0, q0.y));
                             o4.z = __fadd_rn(__fmul_rn(c1, q1.z), __fmul_rn(c0, q0.z));
@@ -359,34 +378,62 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         __syncwarp();
                     }
                 } else {
+                // software pipeline: the TMEM read of the NEXT 8-column block is in flight while this one is computed
+                // and stored (a tcgen05.ld round trip measured ~370 cycles per iteration when taken serially)
+                float n0[8], n1[8];
+                if (half * 8 < H) {
+                    tmem_ld8(t_row + (uint32_t)(half * 8), n0);
+                    tmem_ld8(t_row + (uint32_t)(H + half * 8), n1);
+                }
                 for (int c = half * 8; c < H; c += 16) {
-                    float p0[8], p1[8];
-                    tmem_ld8(t_row + (uint32_t)c, p0);
-                    tmem_ld8(t_row + (uint32_t)(H + c), p1);
+                    const bool dbg_on = P.dbg && threadIdx.x == 0 && it == 1 && c < 32;     // CTA 0 / warp 0, second tile
+                    if (dbg_on) stamp(P.dbg, 210 + (c >> 4) * 4);
                     const float4 ba0 = ldg_f4(P.b0 + c), ba1 = ldg_f4(P.b0 + c + 4);   // biases: 512 B, L1 resident
                     const float4 bb0 = ldg_f4(P.b1 + c), bb1 = ldg_f4(P.b1 + c + 4);
                     const float bA[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
                     const float bB[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
                     tmem_ld_wait();
+                    float p0[8], p1[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) p0[u] = n0[u], p1[u] = n1[u];
+                    if (c + 16 < H) {
+                        tmem_ld8(t_row + (uint32_t)(c + 16), n0);
+                        tmem_ld8(t_row + (uint32_t)(H + c + 16), n1);
+                    } else {                        // last TMEM read of this tile: hand the accumulator back now
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(tempty + acc));
+                        released = true;
+                    }
+                    if (dbg_on) stamp(P.dbg, 211 + (c >> 4) * 4);
                     if (row_ok) {
                         float o[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            p0[u] = act_fwd(p0[u] + bA[u], P.act);
-                            p1[u] = act_fwd(p1[u] + bB[u], P.act);
+                            p0[u] = act_fwd(p0[u] + bA[u], ACT);
+                            p1[u] = act_fwd(p1[u] + bB[u], ACT);
                             o[u] = __fadd_rn(__fmul_rn(c1, p1[u]), __fmul_rn(c0, p0[u]));
                         }
-                        float4* po = reinterpret_cast<float4*>(P.out + row * P.ldo + c);
-                        po[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        po[1] = make_float4(o[4], o[5], o[6], o[7]);
-                        if (P.acts) {
-                            float4* pa = reinterpret_cast<float4*>(P.acts + row * (2 * (int64_t)H) + c);
-                            pa[0] = make_float4(p0[0], p0[1], p0[2], p0[3]);
-                            pa[1] = make_float4(p0[4], p0[5], p0[6], p0[7]);
-                            float4* pb = reinterpret_cast<float4*>(P.acts + row * (2 * (int64_t)H) + H + c);
-                            pb[0] = make_float4(p1[0], p1[1], p1[2], p1[3]);
-                            pb[1] = make_float4(p1[4], p1[5], p1[6], p1[7]);
+                        if (dbg_on) stamp(P.dbg, 212 + (c >> 4) * 4);
+                        if (P.wide) {
+                            st_global_256(P.out + row * P.ldo + c, o);
+                            if (P.acts) {
+                                st_global_256(P.acts + row * (2 * (int64_t)H) + c, p0);
+                                st_global_256(P.acts + row * (2 * (int64_t)H) + H + c, p1);
+                            }
+                        } else {
+                            float4* po = reinterpret_cast<float4*>(P.out + row * P.ldo + c);
+                            po[0] = make_float4(o[0], o[1], o[2], o[3]);
+                            po[1] = make_float4(o[4], o[5], o[6], o[7]);
+                            if (P.acts) {
+                                float4* pa = reinterpret_cast<float4*>(P.acts + row * (2 * (int64_t)H) + c);
+                                pa[0] = make_float4(p0[0], p0[1], p0[2], p0[3]);
+                                pa[1] = make_float4(p0[4], p0[5], p0[6], p0[7]);
+                                float4* pb = reinterpret_cast<float4*>(P.acts + row * (2 * (int64_t)H) + H + c);
+                                pb[0] = make_float4(p1[0], p1[1], p1[2], p1[3]);
+                                pb[1] = make_float4(p1[4], p1[5], p1[6], p1[7]);
+                            }
                         }
+                        if (dbg_on) stamp(P.dbg, 213 + (c >> 4) * 4);
                     }
                 }
                 }
@@ -429,10 +476,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     __syncwarp();
                 }
             } else {
+                float nd[8];
+                if (half * 8 < N) tmem_ld8(t_row + (uint32_t)(half * 8), nd);
                 for (int c = half * 8; c < N; c += 16) {
-                    float d[8];
-                    tmem_ld8(t_row + (uint32_t)c, d);
                     tmem_ld_wait();
+                    float d[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) d[u] = nd[u];
+                    if (c + 16 < N) {
+                        tmem_ld8(t_row + (uint32_t)(c + 16), nd);
+                    } else {
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(tempty + acc));
+                        released = true;
+                    }
                     if (row_ok) {
                         float* dst = nullptr;
                         if (c < P.k1) {
@@ -440,8 +497,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         } else if (P.da2) {
                             dst = P.da2 + row * P.ldda2 + (c - P.k1);
                         }
-                        if (dst) {
+                        if (dst && P.wide) {
                             if (c < P.k1 ? P.acc1 : P.acc2) {      // the operand also fed another GEMM: add to its gradient
+                                float o[8];
+                                ld_global_256(dst, o);
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) d[u] += o[u];
+                            }
+                            st_global_256(dst, d);
+                        } else if (dst) {
+                            if (c < P.k1 ? P.acc1 : P.acc2) {
                                 const float4 o0 = reinterpret_cast<const float4*>(dst)[0], o1 = reinterpret_cast<const float4*>(dst)[1];
                                 d[0] += o0.x, d[1] += o0.y, d[2] += o0.z, d[3] += o0.w;
                                 d[4] += o1.x, d[5] += o1.y, d[6] += o1.z, d[7] += o1.w;
@@ -536,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         // dP[row][k..k+3]: k indexes the 2H pre-activation columns (branch 0 | branch 1)
                         const int br = k >= H;
                         rw.g[i] = ldg_f4(P.dout + row * P.lddo + (k - br * H));
-                        if (P.acts) rw.a[i] = ldg_f4(P.acts + row * (2 * (int64_t)H) + k);
+                        if (ACT != GLASS_ACT_NONE) rw.a[i] = ldg_f4(P.acts + row * (2 * (int64_t)H) + k);
                         rw.lab[i] = P.mask[row];
                     }
                 }
@@ -561,10 +626,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                         const float4 am = *reinterpret_cast<const float4*>(s_norm + K + k);
                         const float4 bs = *reinterpret_cast<const float4*>(s_norm + 2 * K + k);
                         const uint32_t nib = rw.lab[i] >> ((q & 7) * 4);
-                        v.x = act_fwd(fmaf(sc.x, v.x - am.x, bs.x), op.act) * ((nib & 1u) ? op.pscale : 0.f);
-                        v.y = act_fwd(fmaf(sc.y, v.y - am.y, bs.y), op.act) * ((nib & 2u) ? op.pscale : 0.f);
-                        v.z = act_fwd(fmaf(sc.z, v.z - am.z, bs.z), op.act) * ((nib & 4u) ? op.pscale : 0.f);
-                        v.w = act_fwd(fmaf(sc.w, v.w - am.w, bs.w), op.act) * ((nib & 8u) ? op.pscale : 0.f);
+                        v.x = fmaf(sc.x, v.x - am.x, bs.x), v.y = fmaf(sc.y, v.y - am.y, bs.y);
+                        v.z = fmaf(sc.z, v.z - am.z, bs.z), v.w = fmaf(sc.w, v.w - am.w, bs.w);
+                        if (op.act != GLASS_ACT_NONE) {      // one uniform branch per chunk, not two per element
+                            v.x = act_fwd(v.x, op.act), v.y = act_fwd(v.y, op.act);
+                            v.z = act_fwd(v.z, op.act), v.w = act_fwd(v.w, op.act);
+                        }
+                        v.x *= (nib & 1u) ? op.pscale : 0.f, v.y *= (nib & 2u) ? op.pscale : 0.f;
+                        v.z *= (nib & 4u) ? op.pscale : 0.f, v.w *= (nib & 8u) ? op.pscale : 0.f;
                     }
                 }
                 if (BWD) {
@@ -572,11 +641,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     const int br = (kb_of_slot * KBF + (q & 7) * 4) >= H;
                     const float c = rw.lab[i] > 1u ? 0.f : (((rw.lab[i] != 0) == (br != 0)) ? P.z : 1.f - P.z);
                     v.x *= c, v.y *= c, v.z *= c, v.w *= c;
-                    if (P.acts) {
-                        v.x *= act_grad_from_out(rw.a[i].x, P.act);
-                        v.y *= act_grad_from_out(rw.a[i].y, P.act);
-                        v.z *= act_grad_from_out(rw.a[i].z, P.act);
-                        v.w *= act_grad_from_out(rw.a[i].w, P.act);
+                    if (ACT != GLASS_ACT_NONE) {
+                        v.x *= act_grad_from_out(rw.a[i].x, ACT);
+                        v.y *= act_grad_from_out(rw.a[i].y, ACT);
+                        v.z *= act_grad_from_out(rw.a[i].z, ACT);
+                        v.w *= act_grad_from_out(rw.a[i].w, ACT);
                     }
                 }
                 float4 hi, lo;
@@ -669,7 +738,7 @@ __device__ __forceinline__ uint32_t swz_mn(int mn, int i) {
     return (uint32_t)((mn >> 5) * 4096 + (i >> 2) * 512 + (i & 3) * 128 + ((((c16 >> 1) ^ (i & 3)) << 5) | ((c16 & 1) << 4)));
 }
 
-template <bool NORM>
+template <bool NORM, int ACT>
 __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -775,7 +844,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
                 rw.lab[t] = 2u;
                 if (row < m_hi) {
                     rw.g[t] = ldg_f4(P.dout + row * P.lddo + (j - br * H));
-                    if (P.acts) rw.a[t] = ldg_f4(P.acts + row * (2 * (int64_t)H) + j);
+                    if (ACT != GLASS_ACT_NONE) rw.a[t] = ldg_f4(P.acts + row * (2 * (int64_t)H) + j);
                     rw.lab[t] = P.mask[row];
                 }
                 const int q = lt + t * kDwLoadThreads;
@@ -807,11 +876,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
                 float4 v = rw.g[t];
                 const float c = rw.lab[t] > 1u ? 0.f : (((rw.lab[t] != 0) == (br != 0)) ? P.z : 1.f - P.z);
                 v.x *= c, v.y *= c, v.z *= c, v.w *= c;
-                if (P.acts) {
-                    v.x *= act_grad_from_out(rw.a[t].x, P.act);
-                    v.y *= act_grad_from_out(rw.a[t].y, P.act);
-                    v.z *= act_grad_from_out(rw.a[t].z, P.act);
-                    v.w *= act_grad_from_out(rw.a[t].w, P.act);
+                if (ACT != GLASS_ACT_NONE) {
+                    v.x *= act_grad_from_out(rw.a[t].x, ACT);
+                    v.y *= act_grad_from_out(rw.a[t].y, ACT);
+                    v.z *= act_grad_from_out(rw.a[t].z, ACT);
+                    v.w *= act_grad_from_out(rw.a[t].w, ACT);
                 }
                 bsum.x += v.x, bsum.y += v.y, bsum.z += v.z, bsum.w += v.w;
                 float4 hi, lo;
@@ -830,10 +899,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
                             const float4 am = *reinterpret_cast<const float4*>(s_norm + K + k);
                             const float4 bs = *reinterpret_cast<const float4*>(s_norm + 2 * K + k);
                             const uint32_t nib = rw.xw[t] >> ((k < P.k1 ? k : k - P.k1) & 31);
-                            xv.x = act_fwd(fmaf(sc.x, xv.x - am.x, bs.x), op.act) * ((nib & 1u) ? op.pscale : 0.f);
-                            xv.y = act_fwd(fmaf(sc.y, xv.y - am.y, bs.y), op.act) * ((nib & 2u) ? op.pscale : 0.f);
-                            xv.z = act_fwd(fmaf(sc.z, xv.z - am.z, bs.z), op.act) * ((nib & 4u) ? op.pscale : 0.f);
-                            xv.w = act_fwd(fmaf(sc.w, xv.w - am.w, bs.w), op.act) * ((nib & 8u) ? op.pscale : 0.f);
+                            xv.x = fmaf(sc.x, xv.x - am.x, bs.x), xv.y = fmaf(sc.y, xv.y - am.y, bs.y);
+                            xv.z = fmaf(sc.z, xv.z - am.z, bs.z), xv.w = fmaf(sc.w, xv.w - am.w, bs.w);
+                            if (op.act != GLASS_ACT_NONE) {
+                                xv.x = act_fwd(xv.x, op.act), xv.y = act_fwd(xv.y, op.act);
+                                xv.z = act_fwd(xv.z, op.act), xv.w = act_fwd(xv.w, op.act);
+                            }
+                            xv.x *= (nib & 1u) ? op.pscale : 0.f, xv.y *= (nib & 2u) ? op.pscale : 0.f;
+                            xv.z *= (nib & 4u) ? op.pscale : 0.f, xv.w *= (nib & 8u) ? op.pscale : 0.f;
                         }
                     }
                     split_tf32(xv, hi, lo);
@@ -880,8 +953,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_pair_dw_tc(const DwParams P) 
 #pragma unroll
                 for (int u = 0; u < 8; ++u) d[u] = 0.f;
             }
-            reinterpret_cast<float4*>(dst + c)[0] = make_float4(d[0], d[1], d[2], d[3]);
-            reinterpret_cast<float4*>(dst + c)[1] = make_float4(d[4], d[5], d[6], d[7]);
+            st_global_256(dst + c, d);              // part_ld % 8 == 0 and the workspace is 256-byte aligned
         }
         tc_fence_before();
         }
@@ -946,22 +1018,39 @@ bool plan(int kdim, int ndim, bool norm, int stage_arrays, int* stages, size_t* 
     return true;
 }
 
+template <bool BWD, bool NORM, int ACT>
+int launch_act(TcParams& P, cudaStream_t st);
+
 template <bool BWD, bool NORM>
 int launch(TcParams& P, cudaStream_t st) {
+    // backward without saved activations behaves like ACT_NONE (the activation derivative is 1)
+    const int act = (BWD && !P.acts) ? GLASS_ACT_NONE : P.act;
+    if (act == GLASS_ACT_ELU) return launch_act<BWD, NORM, GLASS_ACT_ELU>(P, st);
+    if (act == GLASS_ACT_RELU) return launch_act<BWD, NORM, GLASS_ACT_RELU>(P, st);
+    return launch_act<BWD, NORM, GLASS_ACT_NONE>(P, st);
+}
+
+template <bool BWD, bool NORM, int ACT>
+int launch_act(TcParams& P, cudaStream_t st) {
     size_t bytes = 0;
     // staged epilogue: output width (forward: h, backward: k1 + k2 with the a1|a2 boundary on a 16-column block)
     const int out_w = BWD ? P.ndim : P.h;
-    P.staged = (out_w % 32 == 0) && (!BWD || P.k1 % 16 == 0);
-    static const bool no_stage = getenv("GLASS_B200_TC_DIRECT_EPILOGUE") != nullptr;   // A/B switch for measurements
-    if (no_stage) P.staged = 0;
-    const int stage_arrays = P.staged ? ((!BWD && P.acts) ? 3 : 1) : 0;
+    // (measured: no faster than the direct stores -- the epilogue is not bound by its store pattern -- so it is
+    // opt-in, kept for experiments: GLASS_B200_TC_STAGED=1)
+    static const bool want_stage = getenv("GLASS_B200_TC_STAGED") != nullptr;
+    P.staged = want_stage && (out_w % 32 == 0) && (!BWD || P.k1 % 16 == 0);
+    int stage_arrays = P.staged ? ((!BWD && P.acts) ? 3 : 1) : 0;
+    if (P.staged && (!plan(P.kdim, P.ndim, NORM, stage_arrays, &P.stages, &bytes, &P.tmem_cols) || P.stages < 2)) {
+        P.staged = 0;
+        stage_arrays = 0;
+    }
     if (!plan(P.kdim, P.ndim, NORM, stage_arrays, &P.stages, &bytes, &P.tmem_cols)) {
         set_error("pair_linear_mix (tcgen05): shape k=%d n=%d does not fit", P.kdim, P.ndim);
         return GLASS_ERR_UNSUPPORTED;
     }
     static bool attr_done = false;
     if (!attr_done) {
-        GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD, NORM, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_done = true;
     }
     // equal work per CTA: with 128-row tiles 57,333 rows are 448 tiles = 3.03 per SM, i.e. four rounds for a
@@ -982,7 +1071,7 @@ int launch(TcParams& P, cudaStream_t st) {
         GLASS_CUDA(cudaMemset(dbg, 0, 256 * sizeof(long long)));
         P.dbg = dbg;
     }
-    k_pair_tc<BWD, NORM><<<grid, kThreads, bytes, st>>>(P);
+    k_pair_tc<BWD, NORM, ACT><<<grid, kThreads, bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
     if (timeline) {   // debugging aid only: synchronises and prints CTA 0's event times in SM cycles
         long long h[256];
@@ -996,6 +1085,8 @@ int launch(TcParams& P, cudaStream_t st) {
         for (int i = 0; i < 64 && h[80 + i]; ++i) fprintf(stderr, " %lld", h[80 + i] - h[0]);
         fprintf(stderr, "\n  epilogue:");
         for (int i = 0; i < 50 && h[144 + i]; ++i) fprintf(stderr, " %lld", h[144 + i] - h[0]);
+        fprintf(stderr, "\n  epilogue detail (tile 1, warp 0; start / tmem ready / math done / stores issued):");
+        for (int i = 210; i < 218; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : 0);
         fprintf(stderr, "\n");
     }
     return GLASS_OK;
@@ -1012,8 +1103,7 @@ bool pair_tc_supported(int k1, int k2, int h, int64_t lda1, int64_t lda2, const 
     int s;
     size_t b;
     uint32_t c;
-    const int fwd_arrays = (h % 32 == 0) ? 3 : 0, bwd_arrays = ((k1 + k2) % 32 == 0 && k1 % 16 == 0) ? 1 : 0;
-    return plan(k1 + k2, 2 * h, false, fwd_arrays, &s, &b, &c) && plan(2 * h, k1 + k2, false, bwd_arrays, &s, &b, &c);
+    return plan(k1 + k2, 2 * h, false, 0, &s, &b, &c) && plan(2 * h, k1 + k2, false, 0, &s, &b, &c);
 }
 
 static NormOp norm_op(const glass_norm_operand* n) {
@@ -1041,7 +1131,7 @@ bool pair_tc_norm_supported(int k1, int k2, int h) {
     int s;
     size_t b;
     uint32_t c;
-    return plan(K, 2 * h, true, 3, &s, &b, &c) && s >= 2;
+    return plan(K, 2 * h, true, 0, &s, &b, &c) && s >= 2;
 }
 
 int pair_fwd_tc(const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2, int k2, const float* w0,
@@ -1058,6 +1148,8 @@ int pair_fwd_tc(const float* a1, int64_t lda1, int k1, const float* a2, int64_t 
     P.w0 = w0, P.w1 = w1, P.b0 = b0, P.b1 = b1, P.mask = mask, P.z = z, P.act = act, P.h = h, P.n = n;
     P.out = out, P.ldo = ldo, P.acts = acts;
     P.kdim = k1 + k2, P.ndim = 2 * h;
+    P.wide = ldo % 8 == 0 && (uintptr_t)out % 32 == 0 && (!acts || (uintptr_t)acts % 32 == 0) && h % 8 == 0;
+    if (getenv("GLASS_B200_TC_NARROW_STORES")) P.wide = 0;                        // A/B switch for measurements
     P.n1 = norm_op(n1), P.n2 = norm_op(k2 ? n2 : nullptr);
     if (P.n1.stats || P.n2.stats) {
         if (!pair_tc_norm_supported(k1, k2, h)) {
@@ -1083,6 +1175,10 @@ int pair_bwd_dx_tc(const float* dout, int64_t lddo, const float* acts, const flo
     P.da1 = da1, P.ldda1 = ldda1, P.da2 = da2, P.ldda2 = ldda2;
     P.kdim = 2 * h, P.ndim = k1 + k2;
     P.acc1 = acc1, P.acc2 = acc2;
+    P.wide = k1 % 8 == 0 && k2 % 8 == 0 && (!da1 || (ldda1 % 8 == 0 && (uintptr_t)da1 % 32 == 0)) &&
+             (!da2 || (ldda2 % 8 == 0 && (uintptr_t)da2 % 32 == 0));
+    static const bool narrow = getenv("GLASS_B200_TC_NARROW_STORES") != nullptr;   // A/B switch for measurements
+    if (narrow) P.wide = 0;
     return launch<true, false>(P, st);
 }
 
@@ -1103,15 +1199,15 @@ static int64_t dw_tc_rows_per_cta(int64_t n) {
 
 size_t pair_dw_tc_workspace_bytes(int64_t n, int h, int k) {
     const int64_t splits = ceil_div(n > 0 ? n : 1, dw_tc_rows_per_cta(n));
-    return (size_t)splits * 2 * (size_t)h * ((size_t)k + 4) * sizeof(float);
+    return (size_t)splits * 2 * (size_t)h * ((size_t)k + 8) * sizeof(float);
 }
 
 int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const float* a1, int64_t lda1, int k1,
                    const float* a2, int64_t lda2, int k2, const uint8_t* mask, float z, int act, float* dw0, float* db0,
                    float* dw1, float* db1, int64_t n, int h, void* workspace, const glass_norm_operand* n1,
                    const glass_norm_operand* n2, cudaStream_t st) {
-    if (lddo % 4 || !aligned16(dout) || (acts && !aligned16(acts)) || !aligned16(workspace)) {
-        set_error("pair_linear_mix_bwd dW (tcgen05): operands must be 16-byte aligned");
+    if (lddo % 4 || !aligned16(dout) || (acts && !aligned16(acts)) || ((uintptr_t)workspace & 31)) {
+        set_error("pair_linear_mix_bwd dW (tcgen05): operands must be 16-byte (workspace: 32-byte) aligned");
         return GLASS_ERR_UNSUPPORTED;
     }
     const int K = k1 + k2;
@@ -1119,7 +1215,7 @@ int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const flo
     P.dout = dout, P.lddo = lddo, P.acts = acts, P.mask = mask, P.z = z, P.act = act, P.h = h;
     P.a1 = a1, P.lda1 = lda1, P.k1 = k1, P.a2 = a2, P.lda2 = lda2, P.k2 = k2, P.n = n;
     P.part = static_cast<float*>(workspace);
-    P.part_ld = K + 4;
+    P.part_ld = K + 8;            // column K holds the db partial; rows stay 32-byte aligned for 256-bit stores
     P.rows_per_cta = dw_tc_rows_per_cta(n);
     const int splits = (int)ceil_div(n, P.rows_per_cta);
     const size_t stage_bytes = 2 * (size_t)128 * 128 + 2 * (size_t)K * 128;
@@ -1140,15 +1236,28 @@ int pair_bwd_dw_tc(const float* dout, int64_t lddo, const float* acts, const flo
     uint32_t cols = 32;
     while (cols < (uint32_t)K) cols <<= 1;
     P.tmem_cols = cols;
-    static bool attr_done = false;
-    if (!attr_done) {
-        GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_done = true;
-    }
     dim3 grid((unsigned)splits, (unsigned)(2 * h / 128));
-    if (norm) k_pair_dw_tc<true><<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
-    else k_pair_dw_tc<false><<<grid, kDwThreads, fixed + stages * stage_bytes, st>>>(P);
+    const size_t smem = fixed + stages * stage_bytes;
+    const int kact = acts ? act : GLASS_ACT_NONE;
+#define GLASS_DW_GO(NORM_, ACT_)                                                                                   \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            GLASS_CUDA(cudaFuncSetAttribute(k_pair_dw_tc<NORM_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)); \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        k_pair_dw_tc<NORM_, ACT_><<<grid, kDwThreads, smem, st>>>(P);                                              \
+    } while (0)
+    if (norm) {
+        if (kact == GLASS_ACT_ELU) GLASS_DW_GO(true, GLASS_ACT_ELU);
+        else if (kact == GLASS_ACT_RELU) GLASS_DW_GO(true, GLASS_ACT_RELU);
+        else GLASS_DW_GO(true, GLASS_ACT_NONE);
+    } else {
+        if (kact == GLASS_ACT_ELU) GLASS_DW_GO(false, GLASS_ACT_ELU);
+        else if (kact == GLASS_ACT_RELU) GLASS_DW_GO(false, GLASS_ACT_RELU);
+        else GLASS_DW_GO(false, GLASS_ACT_NONE);
+    }
+#undef GLASS_DW_GO
     GLASS_LAUNCH_CHECK();
     const int64_t total = 2 * (int64_t)h * (K + 1);
     k_pair_dw_tc_reduce<<<(unsigned)ceil_div(total, 32), 256, 0, st>>>(P.part, splits, h, K, P.part_ld, dw0, db0, dw1, db1);

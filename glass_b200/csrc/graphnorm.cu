@@ -609,6 +609,287 @@ k_gn_cluster(const float* __restrict__ x, int64_t ldx, const float* __restrict__
     }
 }
 
+
+// ---- large matrices: the whole GraphNorm (forward or backward) as ONE cooperative launch --------------------------
+// The three-kernel pipeline reads its inputs twice (statistics, then the element-wise pass) and pays two extra
+// launches.  57,333 x 64 floats are 99 KB per SM -- they fit in shared memory.  One persistent CTA per SM loads its
+// contiguous slab of rows ONCE (coalesced float4), keeps it in shared memory while it accumulates the column sums,
+// the CTAs exchange 2c fp64 partials through global memory around a grid-wide barrier (added in CTA order ->
+// deterministic), every CTA finalises the per-column constants redundantly, and the element-wise pass runs out of
+// shared memory.  HBM traffic: inputs once + output once.  Backward caches u = dout*keep/(1-p)*act'(pre) and x.
+// Rows that do not fit the cache (wide matrices) are simply read again from L2 in the second phase.
+constexpr int kCoopThreads = 1024;
+constexpr int kCoopWarps = kCoopThreads / 32;
+
+// reduction scratch (doubles): per-warp partials in phase 1, per-part totals after the grid barrier
+__host__ __device__ inline int coop_red_doubles(int c) {
+    const int cvn = c / 4, wcv = cvn < 32 ? cvn : 32;
+    const int a = kCoopWarps * wcv * 4;
+    return a > kCoopThreads ? a : kCoopThreads;
+}
+
+struct CoopArgs {
+    const float* x;
+    int64_t ldx;
+    const float* dout;      // BWD
+    int64_t lddo;
+    Fin fin;
+    int act;
+    Drop drop;
+    unsigned long long* rng;   // fwd, generator dropout: call id source (advanced by CTA 0)
+    float* out;
+    int64_t ldo;
+    int64_t n;
+    int c;
+    int64_t rows_per_cta;
+    int cache_rows;
+    double* partial;        // [grid][2][c]
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(kCoopThreads, 1) k_gn_coop(const CoopArgs A) {
+    extern __shared__ __align__(16) uint8_t coop_smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int c = A.c, cvn = c >> 2;                       // float4 column vectors per row (kCoopThreads % cvn == 0)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cv = tid % cvn, col = cv * 4;
+    const int rstep = kCoopThreads / cvn;                  // rows advanced per pass of the CTA
+    const int wcv = cvn < 32 ? cvn : 32;                   // distinct column vectors inside one warp
+    // shared memory: [red: kCoopWarps x wcv x 4 doubles][tot: 2c doubles][cst: 8c floats][cache ...]
+    double* s_red = reinterpret_cast<double*>(coop_smem);
+    double* s_tot = s_red + coop_red_doubles(c);
+    float* s_cst = reinterpret_cast<float*>(s_tot + 2 * c);
+    float* s_cache = s_cst + 8 * c;                        // fwd: x slab; bwd: u slab then x slab (cache_rows x c each)
+    const int64_t r0 = (int64_t)blockIdx.x * A.rows_per_cta;
+    const int64_t r1 = min(r0 + A.rows_per_cta, A.n);
+    const int cache_rows = A.cache_rows;
+
+    DropCtx dctx{};
+    unsigned long long call_id = 0;
+    float sc[4], am[4], rs[4], bs[4];
+    if (BWD) {
+        dctx = drop_ctx(A.drop, A.fin.stats, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sc[k] = A.fin.stats[ST_SCALE * c + col + k];
+            am[k] = A.fin.stats[ST_AM * c + col + k];
+            rs[k] = A.fin.stats[ST_RSTD * c + col + k];
+            bs[k] = A.fin.stats[ST_BIAS * c + col + k];
+        }
+    } else if (A.drop.rng) {
+        call_id = *reinterpret_cast<volatile unsigned long long*>(A.rng + 1);   // every CTA reads it before the barrier
+    }
+
+    // u of one float4 chunk (backward): dout * act'(pre) * keep/(1-p)
+    auto make_u = [&](const float4& xv, const float4& gv, int64_t r) {
+        float dm[4];
+        drop_mult<4>(A.drop, dctx, r * (int64_t)c + col, dm);
+        float4 u;
+        u.x = gv.x * act_grad_from_pre(fmaf(sc[0], xv.x - am[0], bs[0]), A.act) * dm[0];
+        u.y = gv.y * act_grad_from_pre(fmaf(sc[1], xv.y - am[1], bs[1]), A.act) * dm[1];
+        u.z = gv.z * act_grad_from_pre(fmaf(sc[2], xv.z - am[2], bs[2]), A.act) * dm[2];
+        u.w = gv.w * act_grad_from_pre(fmaf(sc[3], xv.w - am[3], bs[3]), A.act) * dm[3];
+        return u;
+    };
+
+    // ---- phase 1: load the slab once, cache it, accumulate the column sums
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+    for (int64_t r = r0 + tid / cvn; r < r1; r += rstep) {
+        const float4 xv = ldg_f4(A.x + r * A.ldx + col);
+        const int lr = (int)(r - r0);
+        if (!BWD) {
+            if (lr < cache_rows) *reinterpret_cast<float4*>(s_cache + (int64_t)lr * c + col) = xv;
+            s[0] += (double)xv.x, s[1] += (double)xv.y, s[2] += (double)xv.z, s[3] += (double)xv.w;
+            q[0] += (double)xv.x * (double)xv.x, q[1] += (double)xv.y * (double)xv.y;
+            q[2] += (double)xv.z * (double)xv.z, q[3] += (double)xv.w * (double)xv.w;
+        } else {
+            const float4 gv = ldg_f4(A.dout + r * A.lddo + col);
+            const float4 u = make_u(xv, gv, r);
+            if (lr < cache_rows) {
+                *reinterpret_cast<float4*>(s_cache + (int64_t)lr * c + col) = u;
+                *reinterpret_cast<float4*>(s_cache + ((int64_t)cache_rows + lr) * c + col) = xv;
+            }
+            s[0] += (double)u.x, s[1] += (double)u.y, s[2] += (double)u.z, s[3] += (double)u.w;
+            q[0] += (double)u.x * (double)((xv.x - am[0]) * rs[0]), q[1] += (double)u.y * (double)((xv.y - am[1]) * rs[1]);
+            q[2] += (double)u.z * (double)((xv.z - am[2]) * rs[2]), q[3] += (double)u.w * (double)((xv.w - am[3]) * rs[3]);
+        }
+    }
+    // lanes of a warp with the same column vector, then the warps of the CTA in order (two passes: sums, squares)
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double t = which ? q[k] : s[k];
+            for (int off = cvn; off < 32; off <<= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane < wcv) s_red[(warp * wcv + lane) * 4 + k] = t;
+        }
+        __syncthreads();
+        if (tid < c) {
+            const int tcv = tid >> 2, k = tid & 3;
+            double t = 0.0;
+            if (cvn <= 32) {
+                for (int w = 0; w < kCoopWarps; ++w) t += s_red[(w * wcv + tcv) * 4 + k];
+            } else {            // a warp covers 32 of the cvn column vectors: warp w holds [(32 w) % cvn, +32)
+                const int per = cvn >> 5;
+                for (int w = (tcv >> 5); w < kCoopWarps; w += per) t += s_red[(w * 32 + (tcv & 31)) * 4 + k];
+            }
+            A.partial[((int64_t)blockIdx.x * 2 + which) * c + tid] = t;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    grid.sync();
+
+    // ---- totals (CTA order), per-column constants (every CTA redundantly; CTA 0 publishes).  All 1024 threads take
+    // part: thread (part, j) loads the partials of CTAs part, part + parts, ... (all loads issued before the first
+    // add -- one round of L2 latency instead of one per CTA), the parts are then added in order.
+    {
+        const int parts = min(kCoopThreads / (2 * c), 16);  // >= 4 (c <= 128): at most 37 CTAs per part
+        const int j = tid % (2 * c), part = tid / (2 * c);
+        const int which = j / c, cc = j - which * c;
+        const int nb = (int)gridDim.x;
+        double t = 0.0;
+        if (part < parts) {
+            const int per = (nb + parts - 1) / parts;
+            for (int i0 = 0; i0 < per; i0 += 10) {           // ten independent loads per round
+                double vals[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const int b = part + (i0 + i) * parts;
+                    vals[i] = (i0 + i < per && b < nb) ? __ldcg(A.partial + ((int64_t)b * 2 + which) * c + cc) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 10; ++i) t += vals[i];
+            }
+        }
+        double* s_part = s_red;                               // parts * 2c <= kCoopThreads doubles (coop_red_doubles)
+        if (part < parts) s_part[part * 2 * c + j] = t;
+        __syncthreads();
+        if (tid < 2 * c) {
+            double tot = 0.0;
+            for (int pp = 0; pp < parts; ++pp) tot += s_part[pp * 2 * c + tid];
+            s_tot[tid] = tot;
+        }
+    }
+    __syncthreads();
+    if (tid < c) {
+        Fin f = A.fin;
+        if (!BWD) {
+            f.stats = s_cst;                                 // rows ST_SCALE .. ST_BIAS of a private copy
+            finalize_fwd_col(f, s_tot[tid], s_tot[c + tid], A.n, c, tid);
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int row = 0; row < 5; ++row) A.fin.stats[row * c + tid] = s_cst[row * c + tid];
+            }
+        } else {
+            f.coef = s_cst;
+            finalize_bwd_col(f, s_tot[tid], s_tot[c + tid], A.n, c, tid, blockIdx.x == 0);
+        }
+    }
+    if (!BWD && A.drop.rng && !A.drop.keep && !A.drop.bits) {
+        const unsigned long long seed = A.drop.rng[0];
+        dctx.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        dctx.call_lo = (uint32_t)call_id;
+        dctx.call_hi = c > 1 ? (uint32_t)(call_id >> 32) : 0u;
+        if (blockIdx.x == 0 && tid == 0) {
+            A.rng[1] = call_id + 1;                          // every CTA read the old value before the grid barrier
+            A.fin.stats[ST_RNG * c + 0] = __uint_as_float((uint32_t)call_id);
+            if (c > 1) A.fin.stats[ST_RNG * c + 1] = __uint_as_float((uint32_t)(call_id >> 32));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: element-wise pass out of shared memory
+    float k0[4], k1[4], k2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!BWD) {
+            k0[k] = s_cst[ST_SCALE * c + col + k];
+            k1[k] = s_cst[ST_AM * c + col + k];
+            k2[k] = s_cst[ST_BIAS * c + col + k];
+        } else {
+            k0[k] = s_cst[0 * c + col + k];
+            k1[k] = s_cst[1 * c + col + k];
+            k2[k] = s_cst[2 * c + col + k];
+        }
+    }
+#pragma unroll 2
+    for (int64_t r = r0 + tid / cvn; r < r1; r += rstep) {
+        const int lr = (int)(r - r0);
+        float4 o;
+        if (!BWD) {
+            const float4 xv = lr < cache_rows ? *reinterpret_cast<const float4*>(s_cache + (int64_t)lr * c + col)
+                                              : ldg_f4(A.x + r * A.ldx + col);
+            float dm[4];
+            drop_mult<4>(A.drop, dctx, r * (int64_t)c + col, dm);
+            o.x = act_fwd(fmaf(k0[0], xv.x - k1[0], k2[0]), A.act) * dm[0];
+            o.y = act_fwd(fmaf(k0[1], xv.y - k1[1], k2[1]), A.act) * dm[1];
+            o.z = act_fwd(fmaf(k0[2], xv.z - k1[2], k2[2]), A.act) * dm[2];
+            o.w = act_fwd(fmaf(k0[3], xv.w - k1[3], k2[3]), A.act) * dm[3];
+        } else {
+            float4 u, xv;
+            if (lr < cache_rows) {
+                u = *reinterpret_cast<const float4*>(s_cache + (int64_t)lr * c + col);
+                xv = *reinterpret_cast<const float4*>(s_cache + ((int64_t)cache_rows + lr) * c + col);
+            } else {
+                xv = ldg_f4(A.x + r * A.ldx + col);
+                u = make_u(xv, ldg_f4(A.dout + r * A.lddo + col), r);
+            }
+            o.x = fmaf(k0[0], u.x, fmaf(k1[0], (xv.x - am[0]) * rs[0], k2[0]));
+            o.y = fmaf(k0[1], u.y, fmaf(k1[1], (xv.y - am[1]) * rs[1], k2[1]));
+            o.z = fmaf(k0[2], u.z, fmaf(k1[2], (xv.z - am[2]) * rs[2], k2[2]));
+            o.w = fmaf(k0[3], u.w, fmaf(k1[3], (xv.w - am[3]) * rs[3], k2[3]));
+        }
+        *reinterpret_cast<float4*>(A.out + r * A.ldo + col) = o;
+    }
+}
+
+constexpr size_t kCoopMaxSmem = 232448;   // 227 KB opt-in limit
+
+inline size_t coop_fixed_bytes(int c) {
+    return (size_t)coop_red_doubles(c) * sizeof(double) + (size_t)2 * c * sizeof(double) + (size_t)8 * c * sizeof(float);
+}
+
+// Largest matrices first: one cooperative launch when the column layout allows it.  GLASS_B200_GN_COOP=0 disables.
+inline bool use_coop(int64_t n, int c, bool vec) {
+    static const int on = [] {
+        const char* e = getenv("GLASS_B200_GN_COOP");
+        return e ? atoi(e) : 1;
+    }();
+    static const int64_t min_elems = [] {
+        const char* e = getenv("GLASS_B200_GN_COOP_MIN");
+        return e ? (int64_t)atoll(e) : (int64_t)512 * 1024;
+    }();
+    if (!on || !vec || c > 128 || (kCoopThreads * 4) % c != 0) return false;
+    return n * (int64_t)c >= min_elems;
+}
+
+template <bool BWD>
+int launch_coop(CoopArgs& A, void* workspace, cudaStream_t st) {
+    int grid = sm_count();
+    const int cvn = A.c / 4;
+    const int64_t min_rows = kCoopThreads / cvn;             // at least one pass of the CTA
+    if ((int64_t)grid * min_rows > A.n) grid = (int)std::max<int64_t>(1, A.n / min_rows);
+    A.rows_per_cta = ceil_div(A.n, grid);
+    grid = (int)ceil_div(A.n, A.rows_per_cta);
+    const size_t fixed = coop_fixed_bytes(A.c);
+    const size_t row_bytes = (size_t)A.c * sizeof(float) * (BWD ? 2 : 1);
+    int64_t cache = (int64_t)((kCoopMaxSmem - fixed) / row_bytes);
+    if (cache > A.rows_per_cta) cache = A.rows_per_cta;
+    A.cache_rows = (int)cache;
+    A.partial = static_cast<double*>(workspace);
+    const size_t smem = fixed + (size_t)cache * row_bytes;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GLASS_CUDA(cudaFuncSetAttribute(k_gn_coop<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopMaxSmem));
+        attr_done = true;
+    }
+    void* args[] = {&A};
+    GLASS_CUDA(cudaLaunchCooperativeKernel((const void*)k_gn_coop<BWD>, dim3(grid), dim3(kCoopThreads), args, smem, st));
+    return GLASS_OK;
+}
+
 // Largest matrix (elements) the cluster kernel takes; GLASS_B200_GN_FUSED_MAX overrides (0 disables).
 // Measured fwd+bwd pair, graph replay (scripts/gn_time.py): 10 K elements 19.9 vs 24.1 us (three kernels),
 // 40 K 25.4 vs 26.8, 80 K 29.1 vs 25.2, 160 K 38.7 vs 25.7 -- eight SMs run out of issue slots (Philox, ELU,
@@ -694,7 +975,8 @@ extern "C" size_t glass_graphnorm_workspace_bytes(int64_t n, int c) {
 
 extern "C" int glass_graphnorm_launches(int64_t n, int c) {
     if (n <= 0 || c <= 0) return 0;
-    return use_cluster(n, c, c % 4 == 0 ? 4 : 1) ? 1 : 3;
+    if (use_cluster(n, c, c % 4 == 0 ? 4 : 1)) return 1;
+    return use_coop(n, c, c % 4 == 0) ? 1 : 3;     // (unaligned operands fall back to three launches at run time)
 }
 
 extern "C" size_t glass_dropout_bits_bytes(int64_t n, int c) {
@@ -725,6 +1007,12 @@ extern "C" int glass_graphnorm_fwd(const float* x, int64_t ldx, const float* wei
         else k_gn_cluster<1, false><<<kCl, kClThreads, 0, st>>>(x, ldx, nullptr, 0, fin, act, d, rng, out, ldo, n, c);
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
+    }
+    if (use_coop(n, c, vec)) {   // one cooperative launch; the bits are drawn in-kernel (the `bits` buffer stays unused)
+        CoopArgs A{};
+        A.x = x, A.ldx = ldx, A.fin = fin, A.act = act, A.drop = make_drop(keep, rng, nullptr, drop_p), A.rng = rng;
+        A.out = out, A.ldo = ldo, A.n = n, A.c = c;
+        return launch_coop<false>(A, workspace, st);
     }
     if (vec) k_colsums<4, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial, kPartialLd);
     else k_colsums<1, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial, kPartialLd);
@@ -788,6 +1076,13 @@ extern "C" int glass_graphnorm_bwd(const float* dout, int64_t lddo, const float*
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
     }
+    if (use_coop(n, c, vec)) {
+        CoopArgs A{};
+        A.x = x, A.ldx = ldx, A.dout = dout, A.lddo = lddo, A.fin = fin, A.act = act;
+        A.drop = make_drop(keep, rng, nullptr, drop_p);
+        A.out = dx, A.ldo = lddx, A.n = n, A.c = c;
+        return launch_coop<true>(A, workspace, st);
+    }
     const Drop drop = make_drop(keep, rng, bits, drop_p);
     if (vec) k_colsums<4, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial, kPartialLd);
     else k_colsums<1, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial, kPartialLd);
@@ -826,6 +1121,78 @@ extern "C" int glass_graphnorm_bwd_from_sums(const double* partial, int nblk, in
     const Drop none{};
     if (vec) k_gn_bwd_apply<4, true><<<grid, kThreads, 0, st>>>(u, ldu, x, ldx, stats, bias, coef, GLASS_ACT_NONE, none, dx, lddx, n, c);
     else k_gn_bwd_apply<1, true><<<grid, kThreads, 0, st>>>(u, ldu, x, ldx, stats, bias, coef, GLASS_ACT_NONE, none, dx, lddx, n, c);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
+// ---- two-phase forms for row-partitioned graphs ("GraphNorm column stats need an H-float
+// all-reduce per norm"): a rank computes the partial column sums of ITS rows, the caller adds them across ranks
+// (one 2c-value fp64 all-reduce) and hands the totals back as a one-block partial table with the GLOBAL row count.
+//   forward : glass_graphnorm_partials(x)            -> all-reduce -> glass_graphnorm_stats + glass_graphnorm_apply
+//   backward: glass_graphnorm_bwd_partials(dout, x)  -> all-reduce -> glass_graphnorm_bwd_finish
+// partial layout: partial[(which * c + col) * ldp + blk]; *nblk_host receives the number of blocks written.
+extern "C" int glass_graphnorm_partials_ld(void) { return kPartialLd; }
+
+extern "C" int glass_graphnorm_partials(const float* x, int64_t ldx, int64_t n, int c, double* partial, int ldp,
+                                        int* nblk_host, void* stream) {
+    GLASS_CHECK_ARG(x && partial && nblk_host && n > 0 && c > 0 && ldx >= c && ldp >= kMaxPartialCtas,
+                    "graphnorm_partials: bad arguments");
+    const bool vec = vec_ok(c, {ldx}, {x});
+    const int nblk = partial_ctas(n, c, vec ? 4 : 1);
+    cudaStream_t st = as_stream(stream);
+    if (vec) k_colsums<4, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial, ldp);
+    else k_colsums<1, false><<<nblk, kSumThreads, 0, st>>>(x, ldx, nullptr, 0, nullptr, nullptr, 0, Drop{}, n, c, partial, ldp);
+    GLASS_LAUNCH_CHECK();
+    *nblk_host = nblk;
+    return GLASS_OK;
+}
+
+extern "C" int glass_graphnorm_bwd_partials(const float* dout, int64_t lddo, const float* x, int64_t ldx,
+                                            const float* stats, int act, const uint8_t* keep, float drop_p,
+                                            const uint32_t* bits, int64_t n, int c, double* partial, int ldp,
+                                            int* nblk_host, void* stream) {
+    GLASS_CHECK_ARG(dout && x && stats && partial && nblk_host && n > 0 && c > 0 && ldx >= c && lddo >= c &&
+                        ldp >= kMaxPartialCtas,
+                    "graphnorm_bwd_partials: bad arguments");
+    GLASS_CHECK_ARG(!(drop_p > 0.f && !keep && !bits), "graphnorm_bwd_partials: dropout needs a keep mask or packed bits");
+    const float* bias = stats + ST_BIAS * (int64_t)c;
+    const bool vec = vec_ok(c, {ldx, lddo}, {x, dout});
+    const int nblk = partial_ctas(n, c, vec ? 4 : 1);
+    const Drop drop = make_drop(keep, nullptr, bits, drop_p);
+    cudaStream_t st = as_stream(stream);
+    if (vec) k_colsums<4, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial, ldp);
+    else k_colsums<1, true><<<nblk, kSumThreads, 0, st>>>(x, ldx, dout, lddo, stats, bias, act, drop, n, c, partial, ldp);
+    GLASS_LAUNCH_CHECK();
+    *nblk_host = nblk;
+    return GLASS_OK;
+}
+
+// n_total: the GLOBAL row count the totals in `partial` refer to; n: rows of dout / x / dx held here.
+extern "C" int glass_graphnorm_bwd_finish(const double* partial, int nblk, int ldp, int64_t n_total, const float* dout,
+                                          int64_t lddo, const float* x, int64_t ldx, const float* weight,
+                                          const float* mean_scale, const float* stats, int act, const uint8_t* keep,
+                                          float drop_p, const uint32_t* bits, float* dx, int64_t lddx, float* dweight,
+                                          float* dbias, float* dmean_scale, int64_t n, int c, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    GLASS_CHECK_ARG(partial && nblk > 0 && ldp >= nblk && dout && x && weight && mean_scale && stats && dx && dweight &&
+                        dbias && dmean_scale && n > 0 && n_total >= n && c > 0 && ldx >= c && lddo >= c && lddx >= c,
+                    "graphnorm_bwd_finish: bad arguments");
+    if (workspace_bytes < align_up(3 * (size_t)c * sizeof(float), 256) || !workspace) {
+        set_error("graphnorm_bwd_finish: workspace too small");
+        return GLASS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    float* coef = static_cast<float*>(workspace);
+    const float* bias = stats + ST_BIAS * (int64_t)c;
+    Fin fin{};
+    fin.weight = weight, fin.mean_scale = mean_scale, fin.stats = const_cast<float*>(stats), fin.coef = coef;
+    fin.dweight = dweight, fin.dbias = dbias, fin.dmean_scale = dmean_scale;
+    k_gn_finalize<true><<<(unsigned)ceil_div(c, 8), 256, 0, st>>>(partial, nblk, ldp, n_total, c, fin, nullptr, nullptr, 0, 0u);
+    const bool vec = vec_ok(c, {ldx, lddo, lddx}, {x, dout, dx});
+    const Drop drop = make_drop(keep, nullptr, bits, drop_p);
+    const unsigned grid = apply_ctas(n, c, vec ? 4 : 1, kBwdApplyCtasPerSm);
+    if (vec) k_gn_bwd_apply<4, false><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
+    else k_gn_bwd_apply<1, false><<<grid, kThreads, 0, st>>>(dout, lddo, x, ldx, stats, bias, coef, act, drop, dx, lddx, n, c);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

@@ -70,6 +70,7 @@ struct RowWork {
         dst = y + item * ldy;
         return true;                   // a complete row of y
     }
+    __device__ __forceinline__ int64_t row_of(int64_t item) const { return item; }
 };
 struct PlanWork {
     const int32_t* item_begin;
@@ -86,6 +87,7 @@ struct PlanWork {
         dst = d >= 0 ? y + (int64_t)d * ldy : scratch + (int64_t)(-1 - d) * ld_s;
         return d >= 0;                 // scratch rows are partial sums of a split row (k_spmm_combine finishes them)
     }
+    __device__ __forceinline__ int64_t row_of(int64_t item) const { return __ldg(item_dst + item); }   // only if get() was true
 };
 
 // A row group is G x S lanes: lane l of G owns VEC consecutive feature columns per chunk (KCH column
@@ -127,11 +129,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
         colok[k] = EXACT || coff[k] < h;
     }
 
-    // per-thread running sums stay in fp32 (a thread finishes only a handful of rows; fp64 arithmetic in this loop
-    // cost 20 us on the em_user shape), everything above the thread level is added in fp64
-    float st_s[STATS ? KCH * VEC : 1], st_q[STATS ? KCH * VEC : 1];
-#pragma unroll
-    for (int i = 0; i < (STATS ? KCH * VEC : 1); ++i) st_s[i] = st_q[i] = 0.f;
+    // Statistics: every row group keeps fp32 running sums of the rows it finishes in its OWN shared-memory cells
+    // (a group finishes only a handful of rows; keeping the sums in registers instead cost the gather loop its
+    // memory-level parallelism: +14..20 us on the em_user shape); groups and CTAs are then added in fp64.
+    constexpr int NCOL = G * VEC * KCH;
+    __shared__ float s_acc[STATS ? 2 : 1][STATS ? kThreads / GW : 1][STATS ? NCOL : 1];
+    const int grp = threadIdx.x / GW;
+    if (STATS) {
+        for (int i = threadIdx.x; i < 2 * (kThreads / GW) * NCOL; i += kThreads) (&s_acc[0][0][0])[i] = 0.f;
+        __syncthreads();
+    }
 
     for (; item < n_items; item += groups_per_grid) {
         int32_t e_begin, e_end;
@@ -183,34 +190,21 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
                     const float* a = reinterpret_cast<const float*>(&acc[k]);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
-                        st_s[k * VEC + v] += a[v];
-                        st_q[k * VEC + v] = fmaf(a[v], a[v], st_q[k * VEC + v]);
+                        s_acc[0][grp][coff[k] + v] += a[v];
+                        s_acc[1][grp][coff[k] + v] = fmaf(a[v], a[v], s_acc[1][grp][coff[k] + v]);
                     }
                 }
             }
         }
     }
     if (STATS) {
-        // lanes of a warp that own the same columns (same feature lane l), then the warps of the CTA in order
-        __shared__ double s_red[kThreads / 32][G * VEC * KCH];
-        const int warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-#pragma unroll
-            for (int i = 0; i < KCH * VEC; ++i) {
-                double t = (double)(which ? st_q[i] : st_s[i]);
-#pragma unroll
-                for (int off = G; off < 32; off <<= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                if (lane < G) s_red[warp][coff[i / VEC] + (i % VEC)] = t;
-            }
-            __syncthreads();
-            for (int c = threadIdx.x; c < h; c += kThreads) {
-                double t = 0.0;
-#pragma unroll
-                for (int w = 0; w < kThreads / 32; ++w) t += s_red[w][c];
-                partial[((int64_t)which * h + c) * ldp + blockIdx.x] = t;
-            }
-            __syncthreads();
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * h; i += kThreads) {       // groups of the CTA in order -> deterministic
+            const int which = i / h, c = i - which * h;
+            double t = 0.0;
+#pragma unroll 4
+            for (int g = 0; g < kThreads / GW; ++g) t += (double)s_acc[which][g][c];
+            partial[((int64_t)which * h + c) * ldp + blockIdx.x] = t;
         }
     }
 }
@@ -220,12 +214,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
 __global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot,
                                const int32_t* __restrict__ long_cnt, int64_t n_long, const float* __restrict__ scratch,
                                int64_t ld_s, float* __restrict__ y, int64_t ldy, int h, double* __restrict__ partial,
-                               int ldp, int first_blk) {
+                               int ldp, int first_blk, const float* __restrict__ base = nullptr, int64_t ldb = 0) {
     for (int c = threadIdx.x; c < h; c += blockDim.x) {
         double s = 0.0, q = 0.0;
         for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
             const int32_t r = long_row[i], s0 = long_slot[i], cnt = long_cnt[i];
-            float acc = 0.f;
+            float acc = base ? base[(int64_t)r * ldb + c] : 0.f;
             for (int k = 0; k < cnt; ++k) acc += scratch[(int64_t)(s0 + k) * ld_s + c];
             y[(int64_t)r * ldy + c] = acc;
             s += (double)acc;
@@ -234,6 +228,97 @@ __global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32
         if (partial) {
             partial[(int64_t)c * ldp + first_blk + blockIdx.x] = s;
             partial[((int64_t)h + c) * ldp + first_blk + blockIdx.x] = q;
+        }
+    }
+}
+
+// Sparse label correction (reference impl/train.py:20-34 + impl/models.py:161-164).
+// For fixed weights the label-mixed features of two label batches differ only on the labelled rows:
+//   x_b = U + [labelled] * delta,   so   adj @ x_b = adj @ U + adj[:, labelled] @ delta[labelled]
+// with adj @ U (`base`) computed once per evaluation epoch.  This kernel forms, per batch,
+//   y[i, :] = base[i, :] + sum_{e in row i, mask[col[e]] != 0} val[e] * delta[col[e], :]      (CSR order)
+// It streams the column indices (4 bytes per entry), tests the label byte of every neighbour and gathers only
+// for the ~1-2 % labelled ones -- instead of 4*H bytes per entry.  Same statistics epilogue as k_spmm.
+template <int G, bool STATS, class Work>
+__global__ void __launch_bounds__(kThreads) k_spmm_delta(const Work work, const int32_t* __restrict__ col,
+                                                         const float* __restrict__ val, const uint8_t* __restrict__ mask,
+                                                         const float* __restrict__ delta, int64_t ldd,
+                                                         const float* __restrict__ base, int64_t ldb, int64_t n_items,
+                                                         int h, double* __restrict__ partial, int ldp) {
+    const int lane = threadIdx.x & 31;
+    const int l = lane & (G - 1);
+    const int gshift = lane & ~(G - 1);
+    const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const unsigned gmask = gbits << gshift;
+    const int64_t groups_per_grid = (int64_t)gridDim.x * (kThreads / G);
+    const int coff = l * 4;
+    const bool colok = coff < h;
+    float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t item = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; item < n_items; item += groups_per_grid) {
+        int32_t e_begin, e_end;
+        float* yr;
+        const bool full_row = work.get(item, e_begin, e_end, yr);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full_row && colok) acc = ldg_f4(base + work.row_of(item) * ldb + coff);
+        // software pipeline: the next chunk's indices / label bytes are in flight while this chunk's hits are gathered
+        int32_t nc = -1;
+        bool nhit = false;
+        if (e_begin + l < e_end) {
+            nc = __ldg(col + e_begin + l);
+            nhit = __ldg(mask + nc) != 0;
+        }
+        for (int32_t e0 = e_begin; e0 < e_end; e0 += G) {
+            const int32_t c = nc;
+            const bool hit = nhit;
+            nc = -1;
+            nhit = false;
+            if (e0 + G + l < e_end) {
+                nc = __ldg(col + e0 + G + l);
+                nhit = __ldg(mask + nc) != 0;
+            }
+            unsigned hits = (__ballot_sync(gmask, hit) >> gshift) & gbits;
+            const float w = hit ? __ldg(val + e0 + l) : 0.f;
+            while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int32_t cj = __shfl_sync(gmask, c, j, G);
+                const float wj = __shfl_sync(gmask, w, j, G);
+                if (colok) {
+                    const float4 d = ldg_f4(delta + (int64_t)cj * ldd + coff);
+                    acc.x = fmaf(wj, d.x, acc.x), acc.y = fmaf(wj, d.y, acc.y);
+                    acc.z = fmaf(wj, d.z, acc.z), acc.w = fmaf(wj, d.w, acc.w);
+                }
+            }
+        }
+        if (colok) {
+            *reinterpret_cast<float4*>(yr + coff) = acc;
+            if (STATS && full_row) {
+                st_s[0] += acc.x, st_s[1] += acc.y, st_s[2] += acc.z, st_s[3] += acc.w;
+                st_q[0] = fmaf(acc.x, acc.x, st_q[0]), st_q[1] = fmaf(acc.y, acc.y, st_q[1]);
+                st_q[2] = fmaf(acc.z, acc.z, st_q[2]), st_q[3] = fmaf(acc.w, acc.w, st_q[3]);
+            }
+        }
+    }
+    if (STATS) {
+        __shared__ double s_red[kThreads / 32][G * 4];
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double t = (double)(which ? st_q[i] : st_s[i]);
+#pragma unroll
+                for (int off = G; off < 32; off <<= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                if (lane < G) s_red[warp][coff + i] = t;
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < h; c += kThreads) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < kThreads / 32; ++w) t += s_red[w][c];
+                partial[((int64_t)which * h + c) * ldp + blockIdx.x] = t;
+            }
+            __syncthreads();
         }
     }
 }
@@ -416,6 +501,84 @@ extern "C" int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const f
     Stats s{stats_partial, stats_ld, stats_nblk_host};
     return dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, nullptr, stats_partial ? &s : nullptr,
                     as_stream(stream));
+}
+
+// ---- sparse label correction ---------------------------------------------------------------------------------
+namespace glass {
+namespace {
+template <int G>
+int launch_delta(const int32_t* rowptr, const int32_t* col, const float* val, const uint8_t* mask, const float* delta,
+                 int64_t ldd, const float* base, int64_t ldb, float* y, int64_t ldy, int64_t n_rows, int h,
+                 const Plan* plan, const Stats* stats, cudaStream_t st) {
+    const int64_t n_items = plan ? plan->n_items : n_rows;
+    int64_t blocks = ceil_div(n_items, kThreads / G);
+    const int64_t cap = (int64_t)sm_count() * 8 * (stats ? 1 : 4);
+    if (blocks > cap) blocks = cap;
+    const unsigned grid = (unsigned)blocks;
+    const bool comb = plan && plan->n_long > 0;
+    const int n_comb = comb ? (int)std::min<int64_t>(plan->n_long, kCombineCtas) : 0;
+    double* partial = stats ? stats->partial : nullptr;
+    const int ldp = stats ? stats->ldp : 0;
+    if (stats) {
+        if ((int64_t)grid + n_comb > ldp) {
+            set_error("spmm_delta: statistics table too small (ldp %d < %lld blocks)", ldp, (long long)grid + n_comb);
+            return GLASS_ERR_WORKSPACE;
+        }
+        *stats->nblk_host = (int)grid + n_comb;
+    }
+    if (plan) {
+        PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h};
+        if (stats) k_spmm_delta<G, true, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, mask, delta, ldd, base, ldb, n_items, h, partial, ldp);
+        else k_spmm_delta<G, false, PlanWork><<<grid, kThreads, 0, st>>>(w, col, val, mask, delta, ldd, base, ldb, n_items, h, partial, ldp);
+    } else {
+        RowWork w{rowptr, y, ldy};
+        if (stats) k_spmm_delta<G, true, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, mask, delta, ldd, base, ldb, n_items, h, partial, ldp);
+        else k_spmm_delta<G, false, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, mask, delta, ldd, base, ldb, n_items, h, partial, ldp);
+    }
+    GLASS_LAUNCH_CHECK();
+    if (comb) {
+        const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
+        k_spmm_combine<<<(unsigned)n_comb, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long,
+                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, (int)grid,
+                                                           base, ldb);
+        GLASS_LAUNCH_CHECK();
+    }
+    return GLASS_OK;
+}
+}  // namespace
+}  // namespace glass
+
+extern "C" int glass_spmm_delta(const int32_t* rowptr, const int32_t* col, const float* val, const uint8_t* mask,
+                                const float* delta, int64_t ldd, const float* base, int64_t ldb, float* y, int64_t ldy,
+                                int64_t n_rows, int h, const int32_t* item_begin, const int32_t* item_end,
+                                const int32_t* item_dst, int64_t n_items, const int32_t* long_row,
+                                const int32_t* long_slot, const int32_t* long_cnt, int64_t n_long, float* scratch,
+                                double* stats_partial, int stats_ld, int* stats_nblk_host, void* stream) {
+    GLASS_CHECK_ARG(col && val && mask && delta && base && y && n_rows >= 0 && h > 0 && ldd >= h && ldb >= h && ldy >= h,
+                    "spmm_delta: bad arguments");
+    GLASS_CHECK_ARG(h % 4 == 0 && h <= 128 && ldd % 4 == 0 && ldb % 4 == 0 && ldy % 4 == 0 &&
+                        ((uintptr_t)delta | (uintptr_t)base | (uintptr_t)y | (uintptr_t)scratch) % 16 == 0,
+                    "spmm_delta: needs h %% 4 == 0, h <= 128 and 16-byte aligned rows");
+    const bool planned = item_begin != nullptr;
+    GLASS_CHECK_ARG(planned ? (item_end && item_dst && n_items >= n_rows && (n_long == 0 || (long_row && long_slot && long_cnt && scratch)))
+                            : rowptr != nullptr,
+                    "spmm_delta: give either rowptr or a complete row-split plan");
+    GLASS_CHECK_ARG(!stats_partial || (stats_ld > 0 && stats_nblk_host), "spmm_delta: statistics arguments incomplete");
+    if (stats_nblk_host) *stats_nblk_host = 0;
+    if (n_rows == 0) return GLASS_OK;
+    Plan p{item_begin, item_end, item_dst, n_items, long_row, long_slot, long_cnt, n_long, scratch};
+    Stats s{stats_partial, stats_ld, stats_nblk_host};
+    const Plan* pp = planned ? &p : nullptr;
+    const Stats* sp = stats_partial ? &s : nullptr;
+    cudaStream_t st = as_stream(stream);
+    const int lanes = h / 4;
+#define GO(G) return launch_delta<G>(rowptr, col, val, mask, delta, ldd, base, ldb, y, ldy, n_rows, h, pp, sp, st)
+    if (lanes <= 2) GO(2);
+    if (lanes <= 4) GO(4);
+    if (lanes <= 8) GO(8);
+    if (lanes <= 16) GO(16);
+    GO(32);
+#undef GO
 }
 
 // ---- row-splitting plan (init path; reads rowptr back to the host) ------------------------------------

@@ -70,12 +70,27 @@ class GraphedTrainStep:
         import torch.distributed as dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate
-        # pass); with several ranks GradAverager averages them with two NCCL all-reduces (table + the rest).
+        # autograd hands each parameter its freshly written gradient tensor (no zero-fill, no accumulate pass).
+        # Several ranks: glass_b200.dp.SymmetricGradExchange (one fused reduce-scatter + Adam + all-gather launch over
+        # NVLink peer memory); GLASS_B200_DP=nccl keeps the round-1 path (NCCL all-reduce, then Adam).
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.averager = GradAverager(self.params, group) if self.world > 1 else None
+        self.averager = None
         from .optim import FusedAdam
-        self.opt = FusedAdam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        import os
+        self.dp_mode = "none"
+        if self.world > 1 and os.environ.get("GLASS_B200_DP", "symm") == "symm":
+            try:
+                from .dp import SymmetricGradExchange
+                self.opt = SymmetricGradExchange(self.params, lr, betas, eps, weight_decay, group)
+                self.dp_mode = "symm"
+            except (NotImplementedError, ImportError, AttributeError) as e:
+                import warnings
+                warnings.warn(f"symmetric-memory gradient exchange unavailable ({e}); using NCCL all-reduce")
+        if self.dp_mode == "none":
+            if self.world > 1:
+                self.averager = GradAverager(self.params, group)
+                self.dp_mode = "nccl"
+            self.opt = FusedAdam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.lr = self.opt.lr
         self.loss = torch.zeros((), device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -157,6 +172,60 @@ class GraphedForward:
         return self.out
 
 
+class GraphedSharedBaseForward:
+    """Evaluation over MANY label batches (impl/train.py:20-34) with everything that does not depend on the label
+    batch computed once per epoch: normalised input embedding, first-layer transform of
+    both branches, and the dense adj @ U.  Per batch one CUDA-graph replay runs the sparse label correction
+    (ops.spmm_delta), the combine GEMM, deeper layers if any, pooling and the head.  Same logits as GraphedForward
+    up to fp32 re-association (adj @ U + correction instead of one sum).
+
+    refresh() must be called after the weights change (once per evaluation epoch); it rewrites the shared buffers
+    in place, so the captured per-batch graph stays valid."""
+
+    def __init__(self, model, x, edge_index, edge_weight, pos_example: torch.Tensor, z_fn=utils.MaxZOZ, warmup: int = 2):
+        dev = x.device
+        self.model, self.x, self.ei, self.ew, self.z_fn = model, x, edge_index, edge_weight, z_fn
+        self.pos = torch.empty_like(pos_example, device=dev)
+        self.pos.copy_(pos_example)
+        model.eval()
+        self.base = None
+        self.base_graph = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            self.base = tuple(t.clone() for t in model.shared_base(x, edge_index, edge_weight))   # static buffers
+            for _ in range(warmup):
+                self._refresh_eager()
+                self.out = self._batch()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.base_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.base_graph), torch.no_grad():
+            self._refresh_eager()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = self._batch()
+
+    def _refresh_eager(self):
+        fresh = self.model.shared_base(self.x, self.ei, self.ew)
+        for dst, src in zip(self.base, fresh):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+
+    def _batch(self):
+        return self.model.forward_from_base(self.base, self.ei, self.ew, self.pos, self.z_fn(self.x, self.pos))
+
+    def refresh(self):
+        """Recompute the label-independent base for the model's CURRENT weights (one graph replay)."""
+        self.model.eval()
+        self.base_graph.replay()
+
+    def __call__(self, pos: torch.Tensor) -> torch.Tensor:
+        self.pos.copy_(pos, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def train_epoch(step: GraphedTrainStep, batches, sync_each_step: bool = True) -> float:
     """impl/train.py:4-17 over an iterable of (subG_node, y) batches using the captured step."""
     losses = []
@@ -175,6 +244,8 @@ def test_epoch(fwd: GraphedForward, loader, metrics, loss_fn):
     so the result equals train.test on the same loader."""
     from .SubGDataset import epoch_batches
     cap = fwd.pos.shape[0]
+    if hasattr(fwd, "refresh"):      # shared-base evaluator: the weights may have changed since the last epoch
+        fwd.refresh()
     preds, ys = [], []
     for pos, y in epoch_batches(loader):
         n = pos.shape[0]

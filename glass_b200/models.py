@@ -127,6 +127,40 @@ class GLASSConv(nn.Module):
                                    ACT_NONE)                                                # :167-173
 
 
+    # --- multi-label-batch evaluation ---------------------------------------
+    # For FIXED weights, the label-mixed features of impl/models.py:161 differ between two label batches only on
+    # the labelled rows:  x_b = U + [labelled] * delta  with  U = z*p0 + (1-z)*p1,  delta = (2z-1)*(p1 - p0),
+    # so  adj @ x_b = adj @ U + adj[:, labelled] @ delta[labelled]:  one dense SpMM per evaluation epoch, and per
+    # batch a correction over the ~1-2 % labelled columns (ops.spmm_delta).  Exact up to fp32 re-association.
+    @torch.no_grad()
+    def shared_base(self, x_, edge_index, edge_weight):
+        """Label-independent part of this layer for the current weights: (x_, adj @ U, delta)."""
+        if self.adj is None:
+            self.adj = buildAdj(edge_index, edge_weight, x_.shape[0], self.aggr)
+        t0, t1 = self.trans_fns
+        z = float(self.z_ratio)
+        n, h = x_.shape[0], t0.weight.shape[0]
+        if h % 4 or h > 128:
+            raise NotImplementedError(f"shared-base evaluation needs a hidden width that is a multiple of 4 (<= 128), got {h}")
+        none = torch.zeros(n, dtype=torch.uint8, device=x_.device)                 # nobody labelled -> out = U
+        u = torch.empty((n, h), dtype=torch.float32, device=x_.device)
+        acts = torch.empty((n, 2 * h), dtype=torch.float32, device=x_.device)      # p0 | p1
+        ops.pair_linear_mix_into(x_, None, t0.weight, t0.bias, t1.weight, t1.bias, none, z, _act_id(self.activation),
+                                 u, acts)
+        delta = (2.0 * z - 1.0) * (acts[:, h:] - acts[:, :h])
+        return x_, ops.spmm(self.adj, u), delta.contiguous()
+
+    @torch.no_grad()
+    def forward_from_base(self, base, mask):
+        """Evaluation-mode forward of this layer for one label batch given shared_base()."""
+        x_, y_u, delta = base
+        m = _mask_u8(mask)
+        gn = self.gn
+        c0, c1 = self.comb_fns
+        return ops.glass_conv_from_base(self.adj, x_, y_u, delta, m, (gn.weight, gn.bias, gn.mean_scale, gn.eps),
+                                        (c0.weight, c0.bias, c1.weight, c1.bias), self.z_ratio)
+
+
 class EmbZGConv(nn.Module):
     """impl/models.py:177-272: embedding -> GraphNorm -> dropout -> L x GLASSConv (GraphNorm / activation /
     dropout between layers) -> optional JK concat -> final GraphNorm."""
@@ -164,32 +198,55 @@ class EmbZGConv(nn.Module):
             self._id_cache = hit = (key, same)
         return hit[1]
 
-    def forward(self, x, edge_index, edge_weight, z=None):
+    def _mask(self, n, z, device):
+        if z is None:  # every node takes the "labelled" branch, impl/models.py:242-244
+            return torch.ones(n, dtype=torch.uint8, device=device)
+        return ops.label_mask(z)                                                            # :246
+
+    def _input(self, x):
+        """:248-251: embedding lookup -> emb_gn -> dropout."""
         if self.gns is None:
             raise NotImplementedError("gn=False is outside the accelerated GLASS path (GLASSTest.py:150 uses gn=True)")
         n = x.shape[0]
-        if z is None:  # every node takes the "labelled" branch, impl/models.py:242-244
-            mask = torch.ones(n, dtype=torch.uint8, device=x.device)
-        else:
-            mask = ops.label_mask(z)                                                        # :246
-        act = _act_id(self.activation)
         ids = x.reshape(-1)
         if ids.numel() == n and self._identity_lookup(ids):
             h = self.input_emb.weight                                                       # :248, identity gather
         else:
             h = ops.embedding(ids, self.input_emb.weight).reshape(n, -1)                    # :248
-        h = self.emb_gn(h, p=self.dropout, training=self.training)                          # :249-251
+        return self.emb_gn(h, p=self.dropout, training=self.training)                       # :249-251
+
+    def _layers(self, h, edge_index, edge_weight, mask, first=None):
+        """:253-272 from the output of _input on; `first` replaces the call of convs[0] (shared-base evaluation)."""
+        act = _act_id(self.activation)
         xs = []
-        for layer, conv in enumerate(self.convs[:-1]):                                      # :253-259
-            h = conv(h, edge_index, edge_weight, mask)
+        for layer, conv in enumerate(self.convs):
+            h = first(mask) if (layer == 0 and first is not None) else conv(h, edge_index, edge_weight, mask)
             xs.append(h)
-            h = self.gns[layer](h, act=act, p=self.dropout, training=self.training)
-        h = self.convs[-1](h, edge_index, edge_weight, mask)                                # :260
-        xs.append(h)
+            if layer < len(self.convs) - 1:                                                 # :253-259
+                h = self.gns[layer](h, act=act, p=self.dropout, training=self.training)
         last = self.gns[-1]
         if self.jk and len(xs) > 1:                                                         # :263-267
             return ops.graph_norm_cat(xs, last.weight, last.bias, last.mean_scale, last.eps)
         return last(xs[-1])                                                                 # :268-272
+
+    def forward(self, x, edge_index, edge_weight, z=None):
+        h = self._input(x)
+        return self._layers(h, edge_index, edge_weight, self._mask(x.shape[0], z, x.device))
+
+    @torch.no_grad()
+    def shared_base(self, x, edge_index, edge_weight):
+        """Everything of an evaluation pass that does not depend on the label batch (fixed weights): the normalised
+        input embedding and the first layer's adj @ U / delta (GLASSConv.shared_base)."""
+        if self.training:
+            raise RuntimeError("shared_base is an evaluation-mode fast path (dropout must be off)")
+        return self.convs[0].shared_base(self._input(x), edge_index, edge_weight)
+
+    @torch.no_grad()
+    def forward_from_base(self, base, edge_index, edge_weight, z=None):
+        n = base[0].shape[0]
+        mask = self._mask(n, z, base[0].device)
+        return self._layers(None, edge_index, edge_weight, mask,
+                            first=lambda m: self.convs[0].forward_from_base(base, m))
 
 
 # --- pooling --------------------------------------------------------------------------------------
@@ -277,6 +334,19 @@ class _SubgraphModel(nn.Module):
 
 class GLASS(_SubgraphModel):
     """impl/models.py:322-355."""
+
+    @torch.no_grad()
+    def shared_base(self, x, edge_index, edge_weight):
+        n, copies, width = x.shape
+        if copies != 1:
+            raise NotImplementedError("shared-base evaluation handles the single feature copy GLASSTest.py produces")
+        return self.conv.shared_base(x[:, 0, :].reshape(n, width), edge_index, edge_weight)
+
+    @torch.no_grad()
+    def forward_from_base(self, base, edge_index, edge_weight, subG_node, z=None, id=0):
+        """model(x, ei, ew, subG_node, z) in evaluation mode with the label-independent work taken from `base`."""
+        emb = self.conv.forward_from_base(base, edge_index, edge_weight, z)
+        return self.preds[id](self.Pool(emb, subG_node, self.pools[id]))
 
     def Pool(self, emb, subG_node, pool):
         mode = pool.padded_mode() if isinstance(pool, PoolModule) else None

@@ -33,6 +33,16 @@ _gemm_path = {"auto": GEMM_AUTO, "simt": GEMM_SIMT, "tcgen05": GEMM_TCGEN05}[
     os.environ.get("GLASS_B200_GEMM", "auto")]
 
 
+# GLASSConv as one fused chain (operands normalised inside the GEMM loaders) or as separate ops with the
+# single-launch GraphNorm; measured numbers in DESIGN.md section 4.  GLASS_B200_CONV_FUSED=0/1 overrides.
+_conv_fused = os.environ.get("GLASS_B200_CONV_FUSED", "0") != "0"
+
+
+def set_conv_fused(on: bool) -> None:
+    global _conv_fused
+    _conv_fused = bool(on)
+
+
 def set_gemm_path(name: str) -> None:
     """'auto' | 'simt' | 'tcgen05' -- which kernel family evaluates the label-mixed Linear pairs."""
     global _gemm_path
@@ -125,6 +135,27 @@ def _spmm_csr_planned_(col, val, x, y, item_begin, item_end, item_dst, long_row,
 _define("spmm_csr_planned_(Tensor col, Tensor val, Tensor x, Tensor(a!) y, Tensor item_begin, Tensor item_end, "
         "Tensor item_dst, Tensor long_row, Tensor long_slot, Tensor long_cnt, Tensor(b!) scratch, "
         "Tensor(c!)? partial) -> int", _spmm_csr_planned_)
+
+
+def _spmm_delta_(rowptr, col, val, mask, delta, base, y, item_begin, item_end, item_dst, long_row, long_slot, long_cnt,
+                 scratch, partial):
+    """y = base + adj[:, mask] @ delta[mask]  (sparse label correction)."""
+    lib = _lib.load()
+    n_rows, h = y.shape
+    nblk = C.c_int(0)
+    planned = item_begin is not None
+    check(lib.glass_spmm_delta(_p(rowptr), _p(col), _p(val), _p(mask), _p(delta), delta.stride(0), _p(base),
+                               base.stride(0), _p(y), y.stride(0), n_rows, h, _p(item_begin), _p(item_end),
+                               _p(item_dst), item_begin.numel() if planned else 0, _p(long_row), _p(long_slot),
+                               _p(long_cnt), long_row.numel() if planned else 0, _p(scratch), _p(partial),
+                               0 if partial is None else partial.stride(0), C.byref(nblk), _stream()), "spmm_delta")
+    _count(2 if planned else 1)
+    return nblk.value
+
+
+_define("spmm_delta_(Tensor? rowptr, Tensor col, Tensor val, Tensor mask, Tensor delta, Tensor base, Tensor(a!) y, "
+        "Tensor? item_begin, Tensor? item_end, Tensor? item_dst, Tensor? long_row, Tensor? long_slot, Tensor? long_cnt, "
+        "Tensor(b!)? scratch, Tensor(c!)? partial) -> int", _spmm_delta_)
 
 
 def _pair_fwd_(a1, a2, w0, b0, w1, b1, mask, z_ratio, act, path, out, acts):
@@ -494,6 +525,50 @@ def _run_spmm(rowptr, col, val, plan, x, y, partial=None) -> int:
                                   plan.long_slot, plan.long_cnt, scratch, partial)
 
 
+def graphnorm_partials(x: torch.Tensor, partial: torch.Tensor) -> int:
+    """Per-block fp64 column sums of x and x^2 of THIS rank's rows (row-partitioned GraphNorm, phase 1)."""
+    lib = _lib.load()
+    nblk = C.c_int(0)
+    check(lib.glass_graphnorm_partials(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(partial), partial.stride(0),
+                                       C.byref(nblk), _stream()), "graphnorm_partials")
+    _count(1)
+    return nblk.value
+
+
+def graphnorm_bwd_partials(dout, x, stats, act, keep, drop_p, bits, partial) -> int:
+    lib = _lib.load()
+    nblk = C.c_int(0)
+    check(lib.glass_graphnorm_bwd_partials(_p(dout), dout.stride(0), _p(x), x.stride(0), _p(stats), act, _p(keep),
+                                           drop_p, _p(bits), x.shape[0], x.shape[1], _p(partial), partial.stride(0),
+                                           C.byref(nblk), _stream()), "graphnorm_bwd_partials")
+    _count(1)
+    return nblk.value
+
+
+def graphnorm_bwd_finish(total, n_total, dout, x, weight, mean_scale, stats, act, keep, drop_p, bits, dx, dw, db, da):
+    """Row-partitioned GraphNorm backward, phase 2: `total` [2c, 1] = S1 | S2 summed over all ranks."""
+    lib = _lib.load()
+    n, c = x.shape
+    ws = torch.empty(lib.glass_graphnorm_workspace_bytes(n, c), dtype=torch.uint8, device=x.device)
+    check(lib.glass_graphnorm_bwd_finish(_p(total), 1, total.stride(0), n_total, _p(dout), dout.stride(0), _p(x),
+                                         x.stride(0), _p(weight), _p(mean_scale), _p(stats), act, _p(keep), drop_p,
+                                         _p(bits), _p(dx), dx.stride(0), _p(dw), _p(db), _p(da), n, c, _p(ws),
+                                         ws.numel(), _stream()), "graphnorm_bwd_finish")
+    _count(2)
+
+
+def spmm_delta(adj: "CSRAdj", mask: torch.Tensor, delta: torch.Tensor, base: torch.Tensor, y: torch.Tensor,
+               partial: Optional[torch.Tensor] = None) -> int:
+    """y = base + adj[:, mask] @ delta[mask] (no autograd: evaluation only); returns the statistics block count."""
+    plan = adj.plan
+    if plan is None:
+        return _ops.spmm_delta_(adj.rowptr, adj.col, adj.val, mask, delta, base, y, None, None, None, None, None, None,
+                                None, partial)
+    scratch = torch.empty((plan.n_slots, y.shape[1]), dtype=torch.float32, device=y.device)
+    return _ops.spmm_delta_(None, adj.col, adj.val, mask, delta, base, y, plan.item_begin, plan.item_end, plan.item_dst,
+                            plan.long_row, plan.long_slot, plan.long_cnt, scratch, partial)
+
+
 def _stats_table(c: int, device) -> torch.Tensor:
     """fp64 [2*c, ld] table for per-CTA partial column sums produced by a kernel epilogue."""
     return torch.empty((2 * c, _lib.load().glass_spmm_stats_ld()), dtype=torch.float64, device=device)
@@ -647,6 +722,18 @@ def _dropout_source(n: int, c: int, p: float, training: bool, device):
     return float(p), None, _rng_state(device), torch.empty(words, dtype=torch.int32, device=device)
 
 
+_grad_sinks = {}
+
+
+def register_grad_buffer(param: torch.Tensor, buffer: torch.Tensor) -> None:
+    """Have the backward pass write the gradient of `param` straight into `buffer` (same shape, contiguous) when it
+    is produced by a GraphNorm backward -- the N x H embedding table enters the model through emb_gn, and the
+    data-parallel exchange (glass_b200/dp.py) wants its gradient in peer-visible memory without a 14.7 MB copy."""
+    if buffer.shape != param.shape or not buffer.is_contiguous() or buffer.dtype != param.dtype:
+        raise ValueError("gradient buffer must match the parameter (shape, dtype, contiguous)")
+    _grad_sinks[param.data_ptr()] = buffer
+
+
 class _GraphNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mean_scale, eps, act, p, training):
@@ -669,7 +756,11 @@ class _GraphNorm(torch.autograd.Function):
         act, drop_p = ctx.cfg
         dout, _ = _rowmajor(dout)
         n, c = x.shape
-        dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        sink = _grad_sinks.get(x.data_ptr())
+        if sink is not None and sink.shape == x.shape and sink.device == x.device:
+            dx = sink.view(sink.shape)      # a fresh alias: autograd adopts it as .grad without cloning
+        else:
+            dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
         dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
         _ops.graphnorm_bwd_(dout, x, weight, mean_scale, stats, act, keep, drop_p, rng, bits, dx, dw, db, da,
                             _gn_workspace(n, c, x.device))
@@ -805,7 +896,7 @@ def conv_fusable(k_in: int, h: int, path: Optional[int] = None) -> bool:
     """True when one GLASSConv layer (in width k_in, out width h) can run as the fused chain below: the
     tcgen05 kernels with operands normalised on load (glass_pair_norm_operand_supported)."""
     path = _gemm_path if path is None else path
-    if path == GEMM_SIMT:
+    if path == GEMM_SIMT or not _conv_fused:
         return False
     lib = _lib.load()
     return bool(lib.glass_pair_norm_operand_supported(k_in, 0, h)) and bool(lib.glass_pair_norm_operand_supported(h, k_in, h))
@@ -897,6 +988,38 @@ def glass_conv(x_, adj: CSRAdj, trans, gn, comb, mask, z_ratio: float, act: int,
     gw, gb, gms, eps = gn
     return _GlassConv.apply(x_, adj, *trans, gw, gb, gms, *comb, mask, z_ratio, act, eps, p, training,
                             _gemm_path if path is None else path)
+
+
+def pair_linear_mix_into(a1, a2, w0, b0, w1, b1, mask, z_ratio: float, act: int, out, acts=None, path=None):
+    """Forward only, into caller-provided buffers (`acts` [n, 2h] receives the post-activation p0 | p1)."""
+    _ops.pair_linear_mix_fwd_(_req(a1, torch.float32, "a1", 2), a2, w0, b0, w1, b1, _req(mask, torch.uint8, "mask", 1),
+                              float(z_ratio), act, _gemm_path if path is None else path, out, acts)
+    return out
+
+
+def glass_conv_from_base(adj: CSRAdj, x_, y_u, delta, mask, gn, comb, z_ratio: float, path: Optional[int] = None):
+    """Evaluation-mode GLASSConv for one label batch from the shared base (impl/models.py:164-173 with
+    adj @ x = adj @ U + adj[:, labelled] @ delta[labelled]): correction SpMM with the statistics epilogue ->
+    finalize -> comb GEMM with the norm applied on load (or a materialised norm on non-tcgen05 shapes)."""
+    path = _gemm_path if path is None else path
+    gw, gb, gms, eps = gn
+    cw0, cb0, cw1, cb1 = comb
+    n, h = y_u.shape
+    dev = y_u.device
+    y = torch.empty((n, h), dtype=torch.float32, device=dev)
+    partial = _stats_table(h, dev)
+    nblk = spmm_delta(adj, mask, delta, y_u, y, partial)
+    stats = torch.empty((6, h), dtype=torch.float32, device=dev)
+    _ops.graphnorm_stats_(partial, nblk, n, gw, gb, gms, float(eps), None, 0.0, None, None, stats)
+    out = torch.empty((n, cw0.shape[0]), dtype=torch.float32, device=dev)
+    if conv_fusable(x_.shape[1], h, path):
+        _ops.pair_linear_mix_fwd_ex_(y, x_, cw0, cb0, cw1, cb1, mask, float(z_ratio), ACT_NONE, path, out, None,
+                                     stats, None, 0.0, ACT_NONE, None, None, 0.0, ACT_NONE)
+    else:
+        g = torch.empty_like(y)
+        _ops.graphnorm_apply_(y, stats, ACT_NONE, None, 0.0, None, g)
+        _ops.pair_linear_mix_fwd_(g, x_, cw0, cb0, cw1, cb1, mask, float(z_ratio), ACT_NONE, path, out, None)
+    return out
 
 
 class _Embedding(torch.autograd.Function):

@@ -160,3 +160,175 @@ class _PartSpMM(torch.autograd.Function):
         a = part.local
         ops._run_spmm(a.rowptr_t, a.col_t, a.val_t, a.plan_t, gy_full, gx)
         return gx, None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The whole GLASS model on row shards (stress config): GEMMs, label mix and pooling gathers are
+# row-local; per layer one feature all-gather (RowPartitionedAdj.spmm); per GraphNorm one 2C-value fp64 all-reduce of
+# the column sums; the pooled subgraph vectors are summed across ranks (a subgraph's nodes live on any rank).
+# ---------------------------------------------------------------------------------------------------------
+class Comm:
+    """The two collectives the partitioned model needs.  Default: torch.distributed on `group`; tests substitute an
+    in-process implementation (threads standing in for ranks on one GPU)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def _stats_total(partial: torch.Tensor, nblk: int, comm: Comm) -> torch.Tensor:
+    """Per-block partial column sums of this rank -> global totals as a one-block table [2c, 1] (fp64)."""
+    tot = partial[:, :nblk].sum(dim=1, keepdim=True).contiguous()
+    return comm.all_reduce_sum(tot)
+
+
+class _DistGraphNorm(torch.autograd.Function):
+    """dropout(act(GraphNorm(x))) with x distributed by rows: local partial sums, one all-reduce, local apply.
+    The parameter gradients returned here are this rank's 1/P share of the (already global) sums, so that ONE
+    uniform SUM all-reduce over all parameter gradients (PartitionedGLASS.reduce_grads) finishes every gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mean_scale, eps, act, p, training, n_total, comm):
+        lib = ops._lib.load()
+        x, _ = ops._rowmajor(ops._req(x, torch.float32, "x", 2))
+        n, c = x.shape
+        ld = lib.glass_graphnorm_partials_ld()
+        partial = torch.empty((2 * c, ld), dtype=torch.float64, device=x.device)
+        nblk = ops.graphnorm_partials(x, partial)
+        tot = _stats_total(partial, nblk, comm)
+        drop_p, keep, rng, bits = ops._dropout_source(n, c, p, training, x.device)
+        stats = torch.empty((6, c), dtype=torch.float32, device=x.device)
+        ops._ops.graphnorm_stats_(tot, 1, n_total, weight, bias, mean_scale, float(eps), keep, drop_p, rng, bits, stats)
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        ops._ops.graphnorm_apply_(x, stats, act, keep, drop_p, bits, out)
+        ctx.save_for_backward(x, weight, mean_scale, stats, keep, bits)
+        ctx.cfg = (act, drop_p, n_total, comm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, mean_scale, stats, keep, bits = ctx.saved_tensors
+        act, drop_p, n_total, comm = ctx.cfg
+        lib = ops._lib.load()
+        dout, _ = ops._rowmajor(dout)
+        n, c = x.shape
+        partial = torch.empty((2 * c, lib.glass_graphnorm_partials_ld()), dtype=torch.float64, device=x.device)
+        nblk = ops.graphnorm_bwd_partials(dout, x, stats, act, keep, drop_p, bits, partial)
+        tot = _stats_total(partial, nblk, comm)
+        dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        dw, db, da = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
+        ops.graphnorm_bwd_finish(tot, n_total, dout, x, weight, mean_scale, stats, act, keep, drop_p, bits, dx, dw, db, da)
+        inv = 1.0 / comm.world
+        return dx, dw * inv, db * inv, da * inv, None, None, None, None, None, None
+
+
+class _SumAcrossRanks(torch.autograd.Function):
+    """y = sum over ranks of x.  Everything downstream is computed identically on every rank, so the gradient
+    of the sum with respect to this rank's term is the incoming gradient itself."""
+
+    @staticmethod
+    def forward(ctx, x, comm):
+        return comm.all_reduce_sum(x.clone())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class PartitionedGLASS:
+    """Runs a glass_b200.models.GLASS model (its parameters, replicated on every rank) on ONE rank's row shard.
+
+    forward(h_local, subG_node, z): h_local [rows, H] = this rank's rows of the input embedding (a shard of the table
+    -- at stress scale the table itself is sharded), subG_node the GLOBAL padded node ids, z the GLOBAL labels.
+    After loss.backward(), reduce_grads() adds the gradients of the row-local operators (GEMM weights) across ranks;
+    GraphNorm / head gradients were formed from global sums and are scaled so that the same SUM finishes them."""
+
+    def __init__(self, model, part: RowPartitionedAdj, comm: Comm = None):
+        from . import models
+        if not isinstance(model, models.GLASS) or model.conv.gns is None:
+            raise NotImplementedError("PartitionedGLASS wraps models.GLASS(EmbZGConv(..., gn=True), ...)")
+        self.model, self.part = model, part
+        self.comm = comm if comm is not None else Comm(part.group)
+        self.n = part.n
+
+    def _gn(self, gn, x, act=0, p=0.0):
+        return _DistGraphNorm.apply(x, gn.weight, gn.bias, gn.mean_scale, gn.eps, act, p, self.model.training, self.n,
+                                    self.comm)
+
+    def _conv(self, conv, h, mask):
+        from .models import _act_id
+        t0, t1 = conv.trans_fns
+        c0, c1 = conv.comb_fns
+        x = ops.pair_linear_mix(h, None, t0.weight, t0.bias, t1.weight, t1.bias, mask, conv.z_ratio,
+                                _act_id(conv.activation))                                    # impl/models.py:158-162
+        x = self.part.spmm(x)                                                                # :164 (all-gather inside)
+        x = self._gn(conv.gn, x, p=conv.dropout)                                             # :165-166
+        return ops.pair_linear_mix(x, h, c0.weight, c0.bias, c1.weight, c1.bias, mask, conv.z_ratio, 0)   # :167-173
+
+    def node_emb(self, h_local, z=None):
+        from .models import _act_id
+        net, part = self.model.conv, self.part
+        dev = h_local.device
+        if z is None:
+            mask = torch.ones(part.rows, dtype=torch.uint8, device=dev)
+        else:
+            mask = ops.label_mask(z)[part.lo:part.hi].contiguous()
+        act = _act_id(net.activation)
+        h = self._gn(net.emb_gn, h_local, p=net.dropout)                                     # :249-251
+        xs = []
+        for layer, conv in enumerate(net.convs):
+            h = self._conv(conv, h, mask)
+            xs.append(h)
+            if layer < len(net.convs) - 1:
+                h = self._gn(net.gns[layer], h, act=act, p=net.dropout)                      # :257-259
+        last = net.gns[-1]
+        if net.jk and len(xs) > 1:                                                           # :263-267, per column block
+            outs, off = [], 0
+            for t in xs:
+                w = t.shape[1]
+                outs.append(_DistGraphNorm.apply(t, last.weight[off:off + w], last.bias[off:off + w],
+                                                 last.mean_scale[off:off + w], last.eps, 0, 0.0, False, self.n,
+                                                 self.comm))
+                off += w
+            return torch.cat(outs, dim=1)
+        return self._gn(last, xs[-1])
+
+    def pool(self, emb_local, subG_node, pool):
+        """GLASS.Pool over nodes that live on any rank: local segment sums of the owned nodes, summed across ranks."""
+        mode = pool.padded_mode()
+        if mode not in ("sum", "mean", "size"):
+            raise NotImplementedError(f"partitioned pooling supports sum / mean / size, not {mode}")
+        part = self.part
+        own = (subG_node >= part.lo) & (subG_node < part.hi)
+        local = torch.where(own, subG_node - part.lo, torch.full_like(subG_node, -1))
+        s = _SumAcrossRanks.apply(ops.segment_pool(emb_local, local, "sum"), self.comm)
+        cnt = (subG_node >= 0).sum(dim=1, keepdim=True).to(s.dtype)
+        if mode == "mean":
+            return s / cnt.clamp(min=1)
+        if mode == "size":
+            return s * torch.where(cnt > 0, cnt.pow(-0.5), torch.zeros_like(cnt))
+        return s
+
+    def forward(self, h_local, subG_node, z=None, id=0):
+        emb = self.node_emb(h_local, z)
+        return self.model.preds[id](self.pool(emb, subG_node, self.model.pools[id]))
+
+    __call__ = forward
+
+    def reduce_grads(self):
+        """SUM the parameter gradients across ranks (call after backward)."""
+        inv = 1.0 / self.comm.world
+        head = {id(p) for p in self.model.preds.parameters()}
+        for p in self.model.parameters():
+            if p.grad is None:
+                continue
+            if id(p) in head:          # computed identically on every rank from the summed pooled vectors
+                p.grad.mul_(inv)
+            self.comm.all_reduce_sum(p.grad)

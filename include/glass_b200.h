@@ -105,6 +105,20 @@ int glass_spmm_csr_planned(const int32_t* col, const float* val, const float* x,
                            int64_t n_long, float* scratch, double* stats_partial, int stats_ld,
                            int* stats_nblk_host, void* stream);
 
+/* Sparse label correction for multi-label-batch evaluation (reference
+ * impl/train.py:20-34 evaluates every label batch with a full adj @ x).  For fixed weights the mixed features of two
+ * label batches differ only on the labelled rows (impl/models.py:161-162): x_b = U + [mask] * delta, hence
+ *   y[i,:] = base[i,:] + sum_{e in row i, mask[col[e]] != 0} val[e] * delta[col[e], :]     with base = adj @ U
+ * computed ONCE per evaluation epoch.  Streams 4 bytes per stored entry (the column index) and gathers only for
+ * labelled neighbours.  Either rowptr (item_begin == NULL) or a row-split plan as for glass_spmm_csr_planned;
+ * h % 4 == 0, h <= 128.  Optional statistics epilogue as in glass_spmm_csr. */
+int glass_spmm_delta(const int32_t* rowptr, const int32_t* col, const float* val, const uint8_t* mask,
+                     const float* delta, int64_t ldd, const float* base, int64_t ldb, float* y, int64_t ldy,
+                     int64_t n_rows, int h, const int32_t* item_begin, const int32_t* item_end,
+                     const int32_t* item_dst, int64_t n_items, const int32_t* long_row, const int32_t* long_slot,
+                     const int32_t* long_cnt, int64_t n_long, float* scratch, double* stats_partial, int stats_ld,
+                     int* stats_nblk_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Label-mixed pair of Linear layers  (impl/models.py:158-162 with activation, :169-173 without)
  *   p0 = act([a1|a2] W0^T + b0), p1 = act([a1|a2] W1^T + b1)
@@ -219,6 +233,26 @@ int glass_graphnorm_bwd_from_sums(const double* partial, int nblk, int ldp, cons
                                   float* dmean_scale, int64_t n, int c, void* workspace, size_t workspace_bytes,
                                   void* stream);
 
+/* Two-phase forms for ROW-PARTITIONED graphs (stress config): a rank computes the partial
+ * column sums of its own rows, the caller adds them across ranks (one 2c-value fp64 all-reduce) and passes the
+ * totals back as a one-block table together with the GLOBAL row count n_total.
+ *   forward : glass_graphnorm_partials     -> all-reduce -> glass_graphnorm_stats(n = n_total) + glass_graphnorm_apply
+ *   backward: glass_graphnorm_bwd_partials -> all-reduce -> glass_graphnorm_bwd_finish
+ * ldp >= glass_graphnorm_partials_ld(); *nblk_host receives the number of blocks written (host, synchronously).
+ * With generator dropout the bits drawn by glass_graphnorm_stats cover the rank's own n rows. */
+int glass_graphnorm_partials_ld(void);
+int glass_graphnorm_partials(const float* x, int64_t ldx, int64_t n, int c, double* partial, int ldp,
+                             int* nblk_host, void* stream);
+int glass_graphnorm_bwd_partials(const float* dout, int64_t lddo, const float* x, int64_t ldx, const float* stats,
+                                 int act, const uint8_t* keep, float drop_p, const uint32_t* bits, int64_t n, int c,
+                                 double* partial, int ldp, int* nblk_host, void* stream);
+int glass_graphnorm_bwd_finish(const double* partial, int nblk, int ldp, int64_t n_total, const float* dout,
+                               int64_t lddo, const float* x, int64_t ldx, const float* weight,
+                               const float* mean_scale, const float* stats, int act, const uint8_t* keep,
+                               float drop_p, const uint32_t* bits, float* dx, int64_t lddx, float* dweight,
+                               float* dbias, float* dmean_scale, int64_t n, int c, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * nn.Embedding lookup (impl/models.py:248) and its dense gradient.
  * ids int64 [n]; table [rows, h]; out [n, h].  bwd ACCUMULATES into dtable (caller zero-fills).
@@ -274,6 +308,26 @@ int glass_adam_chunk(void);
 int glass_adam_step(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_begin, int64_t n_chunks,
                     const float* lr, float* state, float beta1, float beta2, float eps, float weight_decay,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Label-batch data parallelism (the reference has no distributed code) without a library
+ * collective in the step: reduce-scatter + Adam + all-gather of the embedding table in ONE launch over NVLink peer
+ * memory.  Every rank owns a symmetric (peer-mapped) block [table | table gradient | small gradients | flags];
+ * peer_base is a DEVICE array [world] with this process' mapping of every rank's block, the off_* are byte offsets
+ * into a block (16-byte aligned; the flag area holds glass_dp_flags_bytes() zero-initialised bytes).
+ * The launch waits until every peer's gradients are complete, averages the table gradient of the element range
+ * [own_begin, own_end) in rank order straight from the peers' blocks, applies Adam (same rule / lr / step count as
+ * glass_adam_step, which must run AFTER it in the same stream for the remaining parameters) and stores the new
+ * values into every rank's table; averages the small-gradient blocks into small_out; returns (kernel end) only when
+ * every peer has finished writing this rank's table.  *error is set to 1 if a peer does not answer within ~2 s.
+ * ------------------------------------------------------------------------------------------ */
+int glass_dp_flags_bytes(void);
+int glass_dp_adam_step(int world, int rank, const unsigned long long* peer_base, unsigned long long off_table,
+                       unsigned long long off_grad, unsigned long long off_small, unsigned long long off_flags,
+                       int64_t table_elems, int64_t own_begin, int64_t own_end, int64_t small_elems, float* m,
+                       float* v, float* small_out, const float* lr, const float* state, float beta1, float beta2,
+                       float eps, float weight_decay, unsigned long long* epoch, unsigned* ticket, int* error,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -251,3 +251,24 @@ def test_full_size_spmm_matches_oracle_sparse_mm(name):
     # per-row bound (hub rows of the power-law graph go through the split-row plan)
     rows = (y.detach().cpu() - ref).abs().amax(dim=1) / ref.abs().amax(dim=1).clamp(min=1e-3)
     assert float(rows.max()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["em_user_shaped", "em_user_shaped_powerlaw", "ppi_bp_shaped"])
+def test_full_size_shared_base_evaluation_matches_oracle(name):
+    """Multi-label-batch evaluation on the benchmarked graphs: adj @ U once, the sparse
+    label correction per batch (row-split plan on the power-law graph), against the oracle's plain forward."""
+    from glass_b200 import utils
+    w = _workload(name, "nodeid")
+    g, m = w["g"], w["model"].eval()
+    bs = w["p"]["batch_size"]
+    x, ei, ew = g.x.to(DEV), g.edge_index.to(DEV), g.edge_attr.to(DEV)
+    sd64 = {k: v.double() for k, v in w["sd"].items()}
+    with torch.no_grad():
+        base = m.shared_base(x, ei, ew)
+        for b in range(2):
+            pos = g.pos[b * bs:(b + 1) * bs].contiguous()
+            z_ref = O.max_zero_one(w["n"], pos)
+            exact, _, _ = O.glass_forward(sd64, g.x, w["adj"].double(), pos, z_ref, w["cfg"])
+            posd = pos.to(DEV)
+            got = m.forward_from_base(base, ei, ew, posd, utils.MaxZOZ(x, posd))
+            assert rel_err(got.cpu(), exact) < TOL

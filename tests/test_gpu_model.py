@@ -387,3 +387,73 @@ def test_pretraining_modules_match_reference_golden():
     assert abs(float(loss) - float(d["loss"])) < TOL
     for k, p in m.named_parameters():
         assert rel_err(p.grad.cpu(), d[f"grad.{k}"]) < TOL, k
+
+
+# ------------------------------------------------------------------------------------------
+# multi-label-batch evaluation: shared base + sparse label correction
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["emuser_like", "ppibp_like", "coreness_like", "density_like", "cutratio_like"])
+def test_shared_base_forward_equals_per_batch_forward(name):
+    """adj @ U once + adj[:, labelled] @ delta[labelled] per batch gives the logits of the ordinary forward
+    (and of the reference golden) for several different label batches of the same weights."""
+    from glass_b200 import utils
+    c = load_model_case(name)
+    m = _product_from_case(c).eval()
+    x, ei, ew, pos, z = _dev(c)
+    n = x.shape[0]
+    with torch.no_grad():
+        base = m.shared_base(x, ei, ew)
+        got = m.forward_from_base(base, ei, ew, pos, z)
+        assert rel_err(got.cpu(), c["logits"]) < TOL                    # the unmodified reference's logits
+        g = torch.Generator().manual_seed(4)
+        for _ in range(3):                                                # other label batches, same base
+            p = c["pos"].clone()
+            perm = torch.randperm(n, generator=g)
+            p[p >= 0] = perm[p[p >= 0]]
+            p = p.to(DEV)
+            zz = utils.MaxZOZ(x, p)
+            ref = m(x, ei, ew, p, zz)
+            got = m.forward_from_base(base, ei, ew, p, zz)
+            assert rel_err(got.cpu(), ref.cpu()) < 1e-5
+        # z = None: every node labelled (the correction touches every column)
+        assert rel_err(m.forward_from_base(base, ei, ew, pos, None).cpu(), m(x, ei, ew, pos, None).cpu()) < 5e-5
+
+
+def test_shared_base_eval_epoch_matches_graphed_eval_epoch():
+    """graphed.test_epoch with the shared-base evaluator returns what it returns with the per-batch evaluator; after
+    the weights change, refresh() (called by test_epoch) picks the new ones up."""
+    from glass_b200 import SubGDataset, utils
+    from glass_b200.graphed import GraphedForward, GraphedSharedBaseForward, test_epoch
+    c = load_model_case("emuser_like")
+    x, ei, ew, pos, _ = _dev(c)
+    y = c["y"].to(DEV)
+    reps = 11 // pos.shape[0] + 1
+    pos_all = pos.repeat(reps, 1)[:11].clone()
+    y_all = y.repeat(*([reps] + [1] * (y.dim() - 1)))[:11].clone()
+    for i in range(1, 11):
+        pos_all[i] = pos_all[i].roll(i, dims=0)
+    ds = SubGDataset.GDataset(x, ei, ew, pos_all, y_all)
+    loader = SubGDataset.ZGDataloader(ds, 4, z_fn=utils.MaxZOZ, shuffle=True, drop_last=False)
+    m = _product_from_case(c).eval()
+    loss_fn = O.loss_fn_for(c["cfg"].out_dim == 1)
+    metric = lambda pred, t: float(np.abs(pred).sum())
+    plain = GraphedForward(m, x, ei, ew, pos_all[:4])
+    shared = GraphedSharedBaseForward(m, x, ei, ew, pos_all[:4])
+    for round_ in range(2):
+        torch.manual_seed(5)
+        ref_score, ref_loss = test_epoch(plain, loader, metric, loss_fn)
+        torch.manual_seed(5)
+        score, loss = test_epoch(shared, loader, metric, loss_fn)
+        assert abs(score - ref_score) <= 1e-5 * max(1.0, abs(ref_score))
+        assert abs(float(loss) - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
+        with torch.no_grad():                                             # "one optimizer step later"
+            for prm in m.parameters():
+                prm.add_(0.05 * torch.randn_like(prm))
+
+
+def test_shared_base_unsupported_width_raises():
+    c = load_model_case("component_like")           # H = 17
+    m = _product_from_case(c).eval()
+    x, ei, ew, pos, z = _dev(c)
+    with pytest.raises(NotImplementedError):
+        m.shared_base(x, ei, ew)
