@@ -221,6 +221,85 @@ def spmm_roofline(adj, h: int, reps: int = 20):
             "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0}
 
 
+def kernel_rooflines(model, wl, x, ei, ew, pos, dev, peak_gbs: float):
+    """Isolated timings (L2 flushed before every launch, CUDA events on the launching stream) of the other kernels of
+    the path with their algorithmic bytes: achieved GB/s and the fraction of the measured HBM peak."""
+    from glass_b200 import _lib, ops
+    from glass_b200.optim import FusedAdam
+    p = wl["params"]
+    n, h = int(x.shape[0]), p["hidden_dim"]
+    nnz = int(ei.shape[1])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _ops = torch.ops.glass_b200
+
+    def timed(fn, reps=8):
+        for _ in range(2):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) / reps * 1e3
+
+    out = {}
+
+    def add(name, us, nbytes, launches):
+        out[name] = {"us": round(us, 2), "algorithmic_bytes": int(nbytes), "gbs": round(nbytes / us * 1e-3, 1),
+                     "frac_hbm": round(nbytes / us * 1e-3 / peak_gbs, 4), "launches": launches}
+
+    # csr_build: int64 pairs + weights read, CSR + transposed CSR written (init path, one host sync inside)
+    add("csr_build", timed(lambda: ops.build_csr(ei, ew, n, p["aggr"]), reps=3), 20 * nnz + 2 * (8 * nnz + 4 * (n + 1)), 9)
+    f32 = dict(dtype=torch.float32, device=dev)
+    a = torch.randn(n, h, **f32)
+    g = torch.randn(n, h, **f32)
+    w, b, ms = torch.ones(h, **f32), torch.zeros(h, **f32), torch.ones(h, **f32)
+    mask = torch.zeros(n, dtype=torch.uint8, device=dev)
+    # GraphNorm forward / backward (one cooperative launch each at this size): x read once, out written once
+    ar = a.clone().requires_grad_(True)
+    add("graphnorm_fwd", timed(lambda: ops.graph_norm(a, w, b, ms, 1e-5, 0, 0.5, True)), 8 * n * h,
+        _lib.load().glass_graphnorm_launches(n, h))
+    y = ops.graph_norm(ar, w, b, ms, 1e-5, 0, 0.5, True)
+    add("graphnorm_bwd", timed(lambda: y.backward(g, retain_graph=True)), 12 * n * h,
+        _lib.load().glass_graphnorm_launches(n, h))
+    # label-mixed Linear pairs (tcgen05): operands read once, out (+ saved activations) written once
+    w0, w1 = torch.randn(h, h, **f32) / 8, torch.randn(h, h, **f32) / 8
+    c0, c1 = torch.randn(h, 2 * h, **f32) / 11, torch.randn(h, 2 * h, **f32) / 11
+    b0, b1 = torch.zeros(h, **f32), torch.zeros(h, **f32)
+    o = torch.empty(n, h, **f32)
+    acts = torch.empty(n, 2 * h, **f32)
+    path = _lib.GEMM_AUTO
+    add("pair_trans_fwd", timed(lambda: _ops.pair_linear_mix_fwd_(a, None, w0, b0, w1, b1, mask, 0.75, 2, path, o, acts)),
+        4 * n * (h + h + 2 * h), 1)
+    add("pair_comb_fwd", timed(lambda: _ops.pair_linear_mix_fwd_(a, g, c0, b0, c1, b1, mask, 0.75, 0, path, o, None)),
+        4 * n * (2 * h + h), 1)
+    ws = torch.empty(_lib.load().glass_pair_linear_mix_bwd_workspace_bytes(n, h, 2 * h), dtype=torch.uint8, device=dev)
+    da1, da2 = torch.empty(n, h, **f32), torch.empty(n, h, **f32)
+    dw0, dw1, db0, db1 = torch.empty_like(c0), torch.empty_like(c1), torch.empty(h, **f32), torch.empty(h, **f32)
+    add("pair_comb_bwd", timed(lambda: _ops.pair_linear_mix_bwd_(o, None, a, g, c0, c1, mask, 0.75, 0, path, da1, da2, dw0,
+                                                                db0, dw1, db1, ws)), 4 * n * (h + 2 * h + 2 * h) + 4 * n * (h + 2 * h), 3)
+    # pooling over one label batch: ids + gathered rows + output forward; the ordered backward writes every row of demb
+    d = h * p["conv_layer"]
+    emb = torch.randn(n, d, **f32).requires_grad_(True)
+    n_valid = int((pos >= 0).sum())
+    add("segment_pool_fwd", timed(lambda: ops.segment_pool(emb, pos, p["pool"])), 8 * pos.numel() + 4 * d * n_valid + 4 * pos.shape[0] * d, 1)
+    pooled = ops.segment_pool(emb, pos, p["pool"])
+    gp = torch.randn_like(pooled)
+    add("segment_pool_bwd", timed(lambda: pooled.backward(gp, retain_graph=True)), 8 * pos.numel() + 4 * n * d + 4 * pos.shape[0] * d, 3)
+    # multi-tensor Adam over all parameters: p, m, v read and written, g read (7 passes)
+    params = [q for q in model.parameters() if q.requires_grad]
+    for q in params:
+        q.grad = torch.zeros_like(q)
+    n_par = sum(q.numel() for q in params)
+    opt = FusedAdam(params, lr=0.0)
+    add("adam", timed(opt.step), 28 * n_par, 1)
+    for q in params:
+        q.grad = None
+    return out
+
+
 def run_product(args):
     import torch.distributed as dist
 
@@ -341,6 +420,12 @@ def run_product(args):
             del sb
         except NotImplementedError as e:
             line["infer_shared_base"] = {"unavailable": str(e)[:200]}
+        if world == 1 and not args.no_kernel_rooflines:
+            try:
+                line["kernel_rooflines"] = kernel_rooflines(model, wl, x, ei, ew, dev_batches[0][0], dev,
+                                                            line["roofline"]["peak"])
+            except Exception as e:  # noqa: BLE001  (secondary numbers must not take the headline line down)
+                line["kernel_rooflines"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             v, per = cpu_port_steps(wl, args.cpu_steps, 1)
             line["cpu_baseline"] = {"value": v, "unit": "subgraphs/s", "cores": torch.get_num_threads(),
@@ -427,6 +512,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short runs of the other BASELINE.json configs (`other_configs` key)")
+    ap.add_argument("--no-kernel-rooflines", action="store_true",
+                    help="skip the isolated timings of csr_build / GraphNorm / pair GEMMs / pooling / Adam (`kernel_rooflines`)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true",
                     help="skip timing the reference's eager torch.sparse op sequence on this GPU (`gpu_eager_baseline` key)")

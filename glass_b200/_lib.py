@@ -27,6 +27,8 @@ PROTOTYPES = {
     "glass_csr_build_workspace_bytes": (_sz, [_i64, _i64]),
     "glass_csr_build": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                C.POINTER(C.c_int64), _vp, _sz, _vp]),
+    "glass_to_undirected_workspace_bytes": (_sz, [_i64]),
+    "glass_to_undirected": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), _vp, _sz, _vp]),
     "glass_spmm_stats_ld": (_i32, []),
     "glass_tune": (_i32, [C.c_char_p, _i32]),
     "glass_spmm_csr": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i32, C.POINTER(C.c_int), _vp]),
@@ -68,8 +70,10 @@ PROTOTYPES = {
                                           _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
     "glass_embedding_fwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "glass_embedding_bwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "glass_embedding_bwd_ordered": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp]),
     "glass_segment_pool_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _i64, _vp]),
-    "glass_segment_pool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "glass_segment_pool_bwd_scratch_bytes": (_sz, [_i64, _i64]),
+    "glass_segment_pool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _vp, _sz, _vp]),
     "glass_segment_pool_batch_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
     "glass_segment_pool_batch_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "glass_adam_chunk": (_i32, []),

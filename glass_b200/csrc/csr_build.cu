@@ -29,13 +29,14 @@ struct Flags {
     int unsorted;   // some key[i] <= key[i-1]
     int bad_index;  // some index outside [0, n_node)
     int nnz_out;
-    int pad;
+    int nonunit;    // some weight != 1.0f (unit weights: degree = entry count, exact in any order)
 };
 
-__global__ void k_pack_keys(const int64_t* __restrict__ ei, int64_t nnz, int64_t n_node,
+__global__ void k_pack_keys(const int64_t* __restrict__ ei, const float* __restrict__ w, int64_t nnz, int64_t n_node,
                             unsigned long long* __restrict__ key, int32_t* __restrict__ idx, Flags* flags) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= nnz) return;
+    if (w[i] != 1.0f) flags->nonunit = 1;
     int64_t r = ei[i], c = ei[nnz + i];
     if (r < 0 || r >= n_node || c < 0 || c >= n_node) {
         flags->bad_index = 1;
@@ -80,12 +81,21 @@ __global__ void k_rowptr(const int32_t* __restrict__ row, int64_t nnz, int64_t n
     for (int64_t r = prev + 1; r <= cur; ++r) rowptr[r] = (int32_t)i;
 }
 
+// Degree = row sum of the raw weights (models.py:90-93).  Unit weights (every dataset the reference produces): the
+// sum of k ones is exactly k in fp32 whatever the order (k < 2^24), so the degree is the entry count -- no loop, no
+// serial walk over a 660-entry coreness row or a 50 K-entry hub of the stress graph.  Other weights keep the
+// sequential fp32 order over the (row, col)-sorted entries that the oracle pins bit for bit.
 __global__ void k_degree(const int32_t* __restrict__ rowptr, const float* __restrict__ ws, int64_t n_node,
-                         int aggr, float* __restrict__ deg, float* __restrict__ dinv) {
+                         int aggr, float* __restrict__ deg, float* __restrict__ dinv, const Flags* __restrict__ flags,
+                         int64_t nnz) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n_node) return;
+    // (bounds are clamped: during the speculative "input is sorted" pass an unsorted input leaves holes in rowptr)
+    const int64_t lo = min(max((int64_t)rowptr[r], (int64_t)0), nnz), hi = min(max((int64_t)rowptr[r + 1], lo), nnz);
     float d = 0.f;
-    for (int32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) d = __fadd_rn(d, ws[e]);  // sequential, sorted order
+    if (flags && !flags->nonunit) d = (float)(hi - lo);
+    else
+        for (int64_t e = lo; e < hi; ++e) d = __fadd_rn(d, ws[e]);                    // sequential, sorted order
     if (d < 0.5f) d = __fadd_rn(d, 1.0f);                                          // models.py:94
     deg[r] = d;
     float inv = 1.0f;
@@ -142,6 +152,57 @@ __global__ void k_gather_transposed(const int32_t* __restrict__ perm, const int3
     int32_t p = perm[i];
     col_t[i] = mrow[p];
     val_t[i] = mval[p];
+}
+
+
+// ---- to_undirected (reference datasets.py:68-71 -> PyG to_undirected: concatenate (row, col) with (col, row), sort by
+// (row, col), add the weights of duplicates) on the device ------------------------------------------------------------
+__global__ void k_pack_sym(const int64_t* __restrict__ ei, int64_t nnz, int64_t n_node, unsigned long long* __restrict__ key,
+                           int32_t* __restrict__ idx, Flags* flags) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    int64_t r = ei[i], c = ei[nnz + i];
+    if (r < 0 || r >= n_node || c < 0 || c >= n_node) {
+        flags->bad_index = 1;
+        r = 0;
+        c = 0;
+    }
+    key[i] = ((unsigned long long)r << 32) | (unsigned long long)(uint32_t)c;
+    key[nnz + i] = ((unsigned long long)c << 32) | (unsigned long long)(uint32_t)r;
+    idx[i] = (int32_t)i;
+    idx[nnz + i] = (int32_t)(nnz + i);  // >= nnz marks the mirrored copy (same weight)
+}
+
+__global__ void k_heads64(const unsigned long long* __restrict__ key, int64_t n, int32_t* __restrict__ head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+
+// one thread per head: adds the weights of its run in sorted (stable) order; also records whether EVERY run has
+// exactly two entries (then the input already was an undirected, duplicate-free edge list)
+__global__ void k_merge_sym(const unsigned long long* __restrict__ key, const int32_t* __restrict__ idx,
+                            const float* __restrict__ w, const int32_t* __restrict__ head, const int32_t* __restrict__ slot,
+                            int64_t n, int64_t* __restrict__ out_row, int64_t* __restrict__ out_col,
+                            float* __restrict__ out_w, Flags* flags) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == n - 1) flags->nnz_out = slot[i] + head[i];
+    if (!head[i]) return;
+    const int32_t half = (int32_t)(n >> 1);
+    auto weight = [&](int32_t k) { return w[k >= half ? k - half : k]; };
+    float acc = weight(idx[i]);
+    int cnt = 1, mirrored = idx[i] >= half ? 1 : 0;
+    for (int64_t j = i + 1; j < n && !head[j]; ++j, ++cnt) {
+        acc = __fadd_rn(acc, weight(idx[j]));
+        mirrored += idx[j] >= half ? 1 : 0;
+    }
+    // undirected and duplicate-free input <=> every entry occurs once as itself and once as the mirror of its reverse
+    if (cnt != 2 || mirrored != 1) flags->unsorted = 1;
+    const int32_t o = slot[i];
+    out_row[o] = (int64_t)(key[i] >> 32);
+    out_col[o] = (int64_t)(key[i] & 0xffffffffu);
+    out_w[o] = acc;
 }
 
 inline int bits_for(int64_t n) {
@@ -256,7 +317,7 @@ extern "C" int glass_csr_build(const int64_t* edge_index, const float* edge_weig
     if (nnz == 0) {
         k_rowptr<<<1, kThreads, 0, st>>>(nullptr, 0, n_node, rowptr);
         k_rowptr<<<1, kThreads, 0, st>>>(nullptr, 0, n_node, rowptr_t);
-        k_degree<<<grid_for(n_node), kThreads, 0, st>>>(rowptr, nullptr, n_node, aggr, deg, dinv);
+        k_degree<<<grid_for(n_node), kThreads, 0, st>>>(rowptr, nullptr, n_node, aggr, deg, dinv, nullptr, 0);
         GLASS_LAUNCH_CHECK();
         GLASS_CUDA(cudaStreamSynchronize(st));
         *nnz_out_host = 0;
@@ -264,64 +325,132 @@ extern "C" int glass_csr_build(const int64_t* edge_index, const float* edge_weig
     }
     GLASS_CHECK_ARG(edge_index && edge_weight && col && val && col_t && val_t, "csr_build: null array");
 
-    // 1. keys + validation
-    k_pack_keys<<<grid_for(nnz), kThreads, 0, st>>>(edge_index, nnz, n_node, key0, idx0, flags);
+    // 1. keys + validation (flags stay on the device: the common case below needs no host round trip)
+    k_pack_keys<<<grid_for(nnz), kThreads, 0, st>>>(edge_index, edge_weight, nnz, n_node, key0, idx0, flags);
+    GLASS_LAUNCH_CHECK();
+
+    // Every dataset the reference produces arrives sorted and duplicate-free (datasets.py:68-71), so the pipeline
+    // first runs SPECULATIVELY as if that were the case and synchronises once at the end; only when the flags say
+    // otherwise (unsorted / duplicate input) is it repeated with the radix sort and the duplicate merge.
+    Flags h{};
+    int64_t nnz_m = nnz;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool sorted_input = pass == 0;
+        // 2. sort when needed
+        const unsigned long long* key_sorted = key0;
+        const int32_t* idx_sorted = idx0;
+        if (!sorted_input) {
+            cub::DoubleBuffer<unsigned long long> kb(key0, key1);
+            cub::DoubleBuffer<int32_t> vb(idx0, idx1);
+            GLASS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)nnz, 0, 32 + bits_for(n_node), st));
+            key_sorted = kb.Current();
+            idx_sorted = vb.Current();
+        }
+        k_unpack_sorted<<<grid_for(nnz), kThreads, 0, st>>>(key_sorted, idx_sorted, edge_weight, nnz, row_s, col_s, w_s);
+        // 3. raw row pointers (into rowptr, reused if no merge is needed) + degree
+        k_rowptr<<<grid_for(nnz + 1), kThreads, 0, st>>>(row_s, nnz, n_node, rowptr);
+        k_degree<<<grid_for(n_node), kThreads, 0, st>>>(rowptr, w_s, n_node, aggr, deg, dinv, flags, nnz);
+        // 4. normalise
+        k_normalise<<<grid_for(nnz), kThreads, 0, st>>>(row_s, col_s, w_s, dinv, nnz, aggr, val_s);
+        GLASS_LAUNCH_CHECK();
+
+        // 5./6. merge duplicates (only possible when the input was not strictly increasing)
+        nnz_m = nnz;
+        const int32_t* mrow_p = row_s;
+        if (!sorted_input) {
+            k_heads<<<grid_for(nnz), kThreads, 0, st>>>(row_s, col_s, nnz, head);
+            GLASS_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, head, slot, (int)nnz, st));
+            k_merge<<<grid_for(nnz), kThreads, 0, st>>>(row_s, col_s, val_s, head, slot, nnz, mrow, col, val, flags);
+            GLASS_LAUNCH_CHECK();
+            GLASS_CUDA(cudaMemcpyAsync(&h, flags, sizeof(Flags), cudaMemcpyDeviceToHost, st));
+            GLASS_CUDA(cudaStreamSynchronize(st));
+            nnz_m = h.nnz_out;
+            mrow_p = mrow;
+            k_rowptr<<<grid_for(nnz_m + 1), kThreads, 0, st>>>(mrow, nnz_m, n_node, rowptr);
+        } else {
+            GLASS_CUDA(cudaMemcpyAsync(col, col_s, 4 * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+            GLASS_CUDA(cudaMemcpyAsync(val, val_s, 4 * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+        }
+
+        // 7. transpose: stable sort by column of the row-sorted merged entries
+        {
+            int32_t* ck0 = reinterpret_cast<int32_t*>(key1);  // key1 / idx1 are scratch in both passes (key0 / idx0 must
+            int32_t* ck1 = ck0 + nnz;                         // survive a speculative first pass for the second one)
+            GLASS_CUDA(cudaMemcpyAsync(ck0, col, 4 * (size_t)nnz_m, cudaMemcpyDeviceToDevice, st));
+            k_iota<<<grid_for(nnz_m), kThreads, 0, st>>>(idx1, nnz_m);
+            cub::DoubleBuffer<int32_t> kb(ck0, ck1);
+            cub::DoubleBuffer<int32_t> vb(idx1, reinterpret_cast<int32_t*>(head));
+            GLASS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)nnz_m, 0, bits_for(n_node), st));
+            k_gather_transposed<<<grid_for(nnz_m), kThreads, 0, st>>>(vb.Current(), mrow_p, val, nnz_m, col_t, val_t);
+            k_rowptr<<<grid_for(nnz_m + 1), kThreads, 0, st>>>(kb.Current(), nnz_m, n_node, rowptr_t);
+            GLASS_LAUNCH_CHECK();
+        }
+        GLASS_CUDA(cudaMemcpyAsync(&h, flags, sizeof(Flags), cudaMemcpyDeviceToHost, st));
+        GLASS_CUDA(cudaStreamSynchronize(st));           // the ONE synchronisation of the common (sorted) case
+        GLASS_CHECK_ARG(!h.bad_index, "csr_build: edge_index has entries outside [0, %lld)", (long long)n_node);
+        if (!sorted_input || !h.unsorted) break;          // speculation held (or this already was the sort pass)
+    }
+    *nnz_out_host = nnz_m;
+    return GLASS_OK;
+}
+
+extern "C" size_t glass_to_undirected_workspace_bytes(int64_t nnz) {
+    if (nnz < 0 || 2 * nnz >= (1ll << 31)) {
+        set_error("to_undirected: nnz=%lld outside the supported range", (long long)nnz);
+        return 0;
+    }
+    Plan p;
+    if (!make_plan(2 * nnz, 1, &p)) {
+        set_error("to_undirected: cub workspace query failed (no CUDA device?)");
+        return 0;
+    }
+    return p.total;
+}
+
+// out_index int64 [2, 2 nnz] (capacity), out_w fp32 [2 nnz]; *nnz_out_host = number of distinct directed entries
+// (the rows of out_index are out_index[0 .. m) and out_index[2 nnz .. 2 nnz + m)); *already_host = 1 when the input was
+// already undirected and duplicate-free (the reference then leaves it untouched, datasets.py:69).
+extern "C" int glass_to_undirected(const int64_t* edge_index, const float* edge_weight, int64_t nnz, int64_t n_node,
+                                   int64_t* out_index, float* out_w, int64_t* nnz_out_host, int* already_host,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t st = as_stream(stream_);
+    GLASS_CHECK_ARG(nnz >= 0 && n_node > 0 && 2 * nnz < (1ll << 31) && n_node < (1ll << 31) && nnz_out_host && already_host,
+                    "to_undirected: bad sizes");
+    *nnz_out_host = 0;
+    *already_host = 0;
+    if (nnz == 0) return GLASS_OK;
+    GLASS_CHECK_ARG(edge_index && edge_weight && out_index && out_w, "to_undirected: null array");
+    const int64_t n2 = 2 * nnz;
+    Plan p;
+    if (!make_plan(n2, 1, &p) || workspace_bytes < p.total || !workspace) {
+        set_error("to_undirected: workspace too small");
+        return GLASS_ERR_WORKSPACE;
+    }
+    char* base = static_cast<char*>(workspace);
+    auto* key0 = reinterpret_cast<unsigned long long*>(base + p.off_key0);
+    auto* key1 = reinterpret_cast<unsigned long long*>(base + p.off_key1);
+    auto* idx0 = reinterpret_cast<int32_t*>(base + p.off_idx0);
+    auto* idx1 = reinterpret_cast<int32_t*>(base + p.off_idx1);
+    auto* head = reinterpret_cast<int32_t*>(base + p.off_head);
+    auto* slot = reinterpret_cast<int32_t*>(base + p.off_slot);
+    auto* flags = reinterpret_cast<Flags*>(base + p.off_flags);
+    void* cub_tmp = base + p.off_cub;
+    size_t cub_bytes = p.cub_bytes;
+    GLASS_CUDA(cudaMemsetAsync(flags, 0, sizeof(Flags), st));
+    k_pack_sym<<<grid_for(nnz), kThreads, 0, st>>>(edge_index, nnz, n_node, key0, idx0, flags);
+    cub::DoubleBuffer<unsigned long long> kb(key0, key1);
+    cub::DoubleBuffer<int32_t> vb(idx0, idx1);
+    GLASS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)n2, 0, 32 + bits_for(n_node), st));
+    k_heads64<<<grid_for(n2), kThreads, 0, st>>>(kb.Current(), n2, head);
+    GLASS_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, head, slot, (int)n2, st));
+    k_merge_sym<<<grid_for(n2), kThreads, 0, st>>>(kb.Current(), vb.Current(), edge_weight, head, slot, n2, out_index,
+                                                  out_index + n2, out_w, flags);
     GLASS_LAUNCH_CHECK();
     Flags h{};
     GLASS_CUDA(cudaMemcpyAsync(&h, flags, sizeof(Flags), cudaMemcpyDeviceToHost, st));
     GLASS_CUDA(cudaStreamSynchronize(st));
-    GLASS_CHECK_ARG(!h.bad_index, "csr_build: edge_index has entries outside [0, %lld)", (long long)n_node);
-
-    // 2. sort when needed
-    const unsigned long long* key_sorted = key0;
-    const int32_t* idx_sorted = idx0;
-    if (h.unsorted) {
-        cub::DoubleBuffer<unsigned long long> kb(key0, key1);
-        cub::DoubleBuffer<int32_t> vb(idx0, idx1);
-        GLASS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)nnz, 0, 32 + bits_for(n_node), st));
-        key_sorted = kb.Current();
-        idx_sorted = vb.Current();
-    }
-    k_unpack_sorted<<<grid_for(nnz), kThreads, 0, st>>>(key_sorted, idx_sorted, edge_weight, nnz, row_s, col_s, w_s);
-    // 3. raw row pointers (into rowptr, reused if no merge is needed) + degree
-    k_rowptr<<<grid_for(nnz + 1), kThreads, 0, st>>>(row_s, nnz, n_node, rowptr);
-    k_degree<<<grid_for(n_node), kThreads, 0, st>>>(rowptr, w_s, n_node, aggr, deg, dinv);
-    // 4. normalise
-    k_normalise<<<grid_for(nnz), kThreads, 0, st>>>(row_s, col_s, w_s, dinv, nnz, aggr, val_s);
-    GLASS_LAUNCH_CHECK();
-
-    // 5./6. merge duplicates (only possible when the input was not strictly increasing)
-    int64_t nnz_m = nnz;
-    const int32_t* mrow_p = row_s;
-    if (h.unsorted) {
-        k_heads<<<grid_for(nnz), kThreads, 0, st>>>(row_s, col_s, nnz, head);
-        GLASS_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, head, slot, (int)nnz, st));
-        k_merge<<<grid_for(nnz), kThreads, 0, st>>>(row_s, col_s, val_s, head, slot, nnz, mrow, col, val, flags);
-        GLASS_LAUNCH_CHECK();
-        GLASS_CUDA(cudaMemcpyAsync(&h, flags, sizeof(Flags), cudaMemcpyDeviceToHost, st));
-        GLASS_CUDA(cudaStreamSynchronize(st));
-        nnz_m = h.nnz_out;
-        mrow_p = mrow;
-        k_rowptr<<<grid_for(nnz_m + 1), kThreads, 0, st>>>(mrow, nnz_m, n_node, rowptr);
-    } else {
-        GLASS_CUDA(cudaMemcpyAsync(col, col_s, 4 * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
-        GLASS_CUDA(cudaMemcpyAsync(val, val_s, 4 * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
-    }
-
-    // 7. transpose: stable sort by column of the row-sorted merged entries
-    {
-        int32_t* ck0 = reinterpret_cast<int32_t*>(key0);  // key buffers are free again
-        int32_t* ck1 = reinterpret_cast<int32_t*>(key1);
-        GLASS_CUDA(cudaMemcpyAsync(ck0, col, 4 * (size_t)nnz_m, cudaMemcpyDeviceToDevice, st));
-        k_iota<<<grid_for(nnz_m), kThreads, 0, st>>>(idx0, nnz_m);
-        cub::DoubleBuffer<int32_t> kb(ck0, ck1);
-        cub::DoubleBuffer<int32_t> vb(idx0, idx1);
-        GLASS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)nnz_m, 0, bits_for(n_node), st));
-        k_gather_transposed<<<grid_for(nnz_m), kThreads, 0, st>>>(vb.Current(), mrow_p, val, nnz_m, col_t, val_t);
-        k_rowptr<<<grid_for(nnz_m + 1), kThreads, 0, st>>>(kb.Current(), nnz_m, n_node, rowptr_t);
-        GLASS_LAUNCH_CHECK();
-    }
-    GLASS_CUDA(cudaStreamSynchronize(st));
-    *nnz_out_host = nnz_m;
+    GLASS_CHECK_ARG(!h.bad_index, "to_undirected: edge_index has entries outside [0, %lld)", (long long)n_node);
+    *nnz_out_host = h.nnz_out;
+    *already_host = (!h.unsorted && h.nnz_out == nnz) ? 1 : 0;
     return GLASS_OK;
 }

@@ -199,6 +199,95 @@ __global__ void k_pool_pad_bwd(const float* __restrict__ dout, int64_t lddo, Pad
     }
 }
 
+// Deterministic backward of the padded pooling (run-to-run bit-reproducible, SURVEY.md section 5 "Determinism").
+// Node-centric: a warp owns 32 consecutive rows of demb and WRITES all of them (zeros for nodes outside the batch --
+// the caller's zero-fill disappears).  k_mark_nodes builds, per step, a byte mark per node and one membership BITMAP
+// per subgraph (b x ceil(N/32) words); for a marked node the warp reads the node's bit of every subgraph (lane b
+// reads bitmap b) and adds coef_b * dout[b, :] for the subgraphs that list it -- in ascending b, one thread per
+// column, no atomics on floats.
+__global__ void k_mark_nodes(const int64_t* __restrict__ pos, int64_t b_cnt, int64_t lmax, uint8_t* __restrict__ mark,
+                             uint32_t* __restrict__ memb, int64_t words, int64_t n_node) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= b_cnt * lmax) return;
+    const int64_t v = pos[i];
+    if (v >= 0 && v < n_node) {
+        mark[v] = 1;
+        atomicOr(memb + (i / lmax) * words + (v >> 5), 1u << (v & 31));      // integer OR: order independent
+    }
+}
+
+constexpr int kOrdWarps = 8;
+__global__ void __launch_bounds__(kOrdWarps * 32)
+k_pool_pad_bwd_ordered(const float* __restrict__ dout, int64_t lddo, const int64_t* __restrict__ pos, int64_t lmax,
+                       int64_t b_cnt, int mode,
+                       const float* __restrict__ cnt, const int32_t* __restrict__ argmax,
+                       const uint8_t* __restrict__ mark, const uint32_t* __restrict__ memb, int64_t words,
+                       float* __restrict__ demb, int64_t ldde, int d, int64_t n_node) {
+    const int lane = threadIdx.x & 31;
+    const int64_t base = ((int64_t)blockIdx.x * kOrdWarps + (threadIdx.x >> 5)) * 32;
+    if (base >= n_node) return;
+    const int64_t mine = base + lane;
+    const unsigned labelled = __ballot_sync(0xffffffffu, mine < n_node && mark[mine] != 0);
+    const int rows = (int)min((int64_t)32, n_node - base);
+    // rows of nodes outside the batch: zeros, as one coalesced sweep over the warp's 32-row block when possible
+    const bool wide = (d % 4 == 0) && (ldde % 4 == 0) && ((uintptr_t)demb % 16 == 0);
+    if (wide) {
+        const int cv = d >> 2;                                 // float4 per row
+        for (int q = lane; q < rows * cv; q += 32) {
+            const int j = q / cv;
+            if (!((labelled >> j) & 1u))
+                *reinterpret_cast<float4*>(demb + (base + j) * ldde + (q - j * cv) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (int j = 0; j < rows; ++j) {
+        const int64_t v = base + j;
+        float* row = demb + v * ldde;
+        if (!((labelled >> j) & 1u)) {
+            if (!wide)
+                for (int c = lane; c < d; c += 32) row[c] = 0.f;
+            continue;
+        }
+        for (int c0 = 0; c0 < d; c0 += 128) {                 // 4 columns per lane and pass
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int64_t b0 = 0; b0 < b_cnt; b0 += 32) {       // 32 subgraphs per step: lane -> subgraph b0 + lane
+                const int64_t bl = b0 + lane;
+                const bool in = bl < b_cnt && ((__ldg(memb + bl * words + (v >> 5)) >> (v & 31)) & 1u);
+                unsigned hits = __ballot_sync(0xffffffffu, in);
+                while (hits) {
+                    const int64_t b = b0 + (__ffs(hits) - 1);
+                    hits &= hits - 1;
+                    if (mode == GLASS_POOL_MAX) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int c = c0 + lane + 32 * k;
+                            if (c < d && argmax[b * (int64_t)d + c] == (int32_t)v) acc[k] += dout[b * lddo + c];
+                        }
+                    } else {
+                        // a padded row may list a node more than once (EdgeGNN pairs (u, u)): count the occurrences
+                        int mult = 0;
+                        for (int64_t l0 = 0; l0 < lmax; l0 += 32)
+                            mult += __popc(__ballot_sync(0xffffffffu, l0 + lane < lmax && __ldg(pos + b * lmax + l0 + lane) == v));
+                        const float coef = bwd_coef(mode, cnt[b]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int c = c0 + lane + 32 * k;
+                            if (c < d) {
+                                const float gc = dout[b * lddo + c] * coef;
+                                for (int m = 0; m < mult; ++m) acc[k] += gc;      // same value the per-entry sum adds
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + lane + 32 * k;
+                if (c < d) row[c] = acc[k];
+            }
+        }
+    }
+}
+
 // (x, batch) variant: every gathered row belongs to exactly one segment -> plain stores, one thread per element.
 __global__ void k_pool_batch_bwd(const float* __restrict__ dout, int64_t lddo, const int64_t* __restrict__ batch,
                                  int64_t m, int mode, const float* __restrict__ cnt, const int32_t* __restrict__ argmax,
@@ -243,9 +332,15 @@ extern "C" int glass_segment_pool_fwd(const float* emb, int64_t lde, const int64
     return GLASS_OK;
 }
 
+// scratch of the ordered backward: b membership bitmaps + one byte mark per node
+extern "C" size_t glass_segment_pool_bwd_scratch_bytes(int64_t b, int64_t n_node) {
+    if (b < 0 || n_node <= 0) return 0;
+    return align_up((size_t)b * (size_t)ceil_div(n_node, 32) * sizeof(uint32_t) + (size_t)n_node, 256);
+}
+
 extern "C" int glass_segment_pool_bwd(const float* dout, int64_t lddo, const int64_t* pos, int64_t b, int64_t lmax,
                                       int mode, const float* cnt, const int32_t* argmax, float* demb, int64_t ldde,
-                                      int d, int64_t n_node, void* stream) {
+                                      int d, int64_t n_node, void* scratch, size_t scratch_bytes, void* stream) {
     if (!mode_ok(mode)) {
         set_error("segment_pool: unknown pool mode %d", mode);
         return GLASS_ERR_UNSUPPORTED;
@@ -253,6 +348,24 @@ extern "C" int glass_segment_pool_bwd(const float* dout, int64_t lddo, const int
     GLASS_CHECK_ARG(dout && pos && cnt && demb && b >= 0 && lmax >= 0 && d > 0 && lddo >= d && ldde >= d && n_node > 0,
                     "segment_pool_bwd: bad arguments");
     GLASS_CHECK_ARG(mode != GLASS_POOL_MAX || argmax, "segment_pool_bwd: MAX needs argmax");
+    if (scratch) {   // ordered (deterministic) variant: writes EVERY row of demb, no zero-fill needed
+        const size_t need = glass_segment_pool_bwd_scratch_bytes(b, n_node);
+        if (scratch_bytes < need) {
+            set_error("segment_pool_bwd: scratch %zu < required %zu", scratch_bytes, need);
+            return GLASS_ERR_WORKSPACE;
+        }
+        cudaStream_t st = as_stream(stream);
+        const int64_t words = ceil_div(n_node, 32);
+        uint32_t* memb = static_cast<uint32_t*>(scratch);
+        uint8_t* mark = static_cast<uint8_t*>(scratch) + (size_t)b * words * sizeof(uint32_t);
+        GLASS_CUDA(cudaMemsetAsync(scratch, 0, need, st));
+        const int64_t n_pos = b * lmax;
+        if (n_pos > 0) k_mark_nodes<<<(unsigned)ceil_div(n_pos, 256), 256, 0, st>>>(pos, b, lmax, mark, memb, words, n_node);
+        k_pool_pad_bwd_ordered<<<(unsigned)ceil_div(n_node, kOrdWarps * 32), kOrdWarps * 32, 0, st>>>(
+            dout, lddo, pos, lmax, b, mode, cnt, argmax, mark, memb, words, demb, ldde, d, n_node);
+        GLASS_LAUNCH_CHECK();
+        return GLASS_OK;
+    }
     if (b == 0) return GLASS_OK;
     PadSeg seg{pos, lmax, n_node};
     k_pool_pad_bwd<<<(unsigned)b, pool_block(d), 0, as_stream(stream)>>>(dout, lddo, seg, mode, cnt, argmax, demb, ldde, d);

@@ -128,10 +128,66 @@ __global__ void k_embed_bwd(const float* __restrict__ dout, int64_t lddo, const 
     }
 }
 
+// Deterministic gradient of the lookup (run-to-run bit-reproducible).  The rows are visited in the order of a
+// stable sort by id (plan built once per id tensor on the host side: perm, and "runs" = stretches of at most 128
+// sorted positions with one id).  Pass 1: one warp per run adds its rows in order (thread per column) into
+// run_sum[run, :].  Pass 2: one warp per distinct id adds the runs of that id in order into dtable[id, :].
+__global__ void k_embed_bwd_runs(const float* __restrict__ dout, int64_t lddo, const int64_t* __restrict__ perm,
+                                 const int32_t* __restrict__ run_begin, const int32_t* __restrict__ run_end,
+                                 int64_t n_runs, float* __restrict__ run_sum, int h) {
+    const int64_t run = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (run >= n_runs) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t b = run_begin[run], e = run_end[run];
+    for (int c = lane; c < h; c += 32) {
+        float acc = 0.f;
+        int32_t p = b;
+        for (; p + 8 <= e; p += 8) {               // eight independent loads in flight, added in order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = dout[__ldg(perm + p + u) * lddo + c];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; p < e; ++p) acc += dout[__ldg(perm + p) * lddo + c];
+        run_sum[run * h + c] = acc;
+    }
+}
+
+__global__ void k_embed_bwd_ids(const float* __restrict__ run_sum, const int64_t* __restrict__ uid,
+                                const int32_t* __restrict__ uid_first_run, const int32_t* __restrict__ uid_runs,
+                                int64_t n_uid, float* __restrict__ dtable, int64_t rows, int h) {
+    const int64_t u = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n_uid) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t id = uid[u];
+    if (id < 0 || id >= rows) return;
+    const int32_t r0 = uid_first_run[u], cnt = uid_runs[u];
+    for (int c = lane; c < h; c += 32) {
+        float acc = 0.f;
+        for (int32_t r = 0; r < cnt; ++r) acc += run_sum[(int64_t)(r0 + r) * h + c];
+        dtable[id * h + c] = acc;
+    }
+}
+
 }  // namespace
 }  // namespace glass
 
 using namespace glass;
+
+extern "C" int glass_embedding_bwd_ordered(const float* dout, int64_t lddo, const int64_t* perm, const int32_t* run_begin,
+                                           const int32_t* run_end, int64_t n_runs, const int64_t* uid,
+                                           const int32_t* uid_first_run, const int32_t* uid_runs, int64_t n_uid,
+                                           float* run_sum, float* dtable, int64_t rows, int h, void* stream) {
+    GLASS_CHECK_ARG(dout && perm && run_begin && run_end && uid && uid_first_run && uid_runs && run_sum && dtable &&
+                        n_runs >= 0 && n_uid >= 0 && rows > 0 && h > 0 && lddo >= h,
+                    "embedding_bwd_ordered: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    if (n_runs > 0) k_embed_bwd_runs<<<(unsigned)ceil_div(n_runs, 8), 256, 0, st>>>(dout, lddo, perm, run_begin, run_end, n_runs, run_sum, h);
+    if (n_uid > 0) k_embed_bwd_ids<<<(unsigned)ceil_div(n_uid, 8), 256, 0, st>>>(run_sum, uid, uid_first_run, uid_runs, n_uid, dtable, rows, h);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
 
 extern "C" int glass_abi_version(void) { return GLASS_B200_ABI_VERSION; }
 extern "C" const char* glass_last_error(void) { return g_err; }

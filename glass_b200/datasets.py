@@ -60,8 +60,13 @@ class BaseGraph:
         return self.x.shape[0]
 
     def to_undirected(self):
+        """datasets.py:68-71.  Edge lists that already live on a GPU are symmetrised / sorted / merged by the CUDA
+        kernels (ops.to_undirected); host tensors take the torch path."""
         n = self.x.shape[0]
-        if not _is_undirected(self.edge_index, n):
+        if self.edge_index.is_cuda:
+            from . import ops
+            self.edge_index, self.edge_attr = ops.to_undirected(self.edge_index, self.edge_attr.to(torch.float32), n)
+        elif not _is_undirected(self.edge_index, n):
             self.edge_index, self.edge_attr = coalesce_undirected(self.edge_index, self.edge_attr, n)
 
     def _degree(self):

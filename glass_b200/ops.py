@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
 
-__all__ = ["CSRAdj", "build_csr", "spmm", "spmm_graph_norm", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
+__all__ = ["CSRAdj", "build_csr", "to_undirected", "spmm", "spmm_graph_norm", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
            "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",
            "set_gemm_path", "launch_count", "reset_launch_count", "manual_seed"]
 
@@ -332,18 +332,20 @@ def _pool_fwd_(emb, pos, mode, out, cnt, argmax):
     _count(1)
 
 
-def _pool_bwd_(dout, pos, mode, cnt, argmax, demb):
+def _pool_bwd_(dout, pos, mode, cnt, argmax, demb, mark):
+    """mark (uint8 [n_node] scratch): deterministic node-centric variant that writes every row of demb."""
     lib = _lib.load()
     b, lmax = pos.shape
     check(lib.glass_segment_pool_bwd(_p(dout), dout.stride(0), _p(pos), b, lmax, mode, _p(cnt), _p(argmax), _p(demb),
-                                     demb.stride(0), demb.shape[1], demb.shape[0], _stream()), "segment_pool_bwd")
-    _count(1)
+                                     demb.stride(0), demb.shape[1], demb.shape[0], _p(mark),
+                                     0 if mark is None else mark.numel(), _stream()), "segment_pool_bwd")
+    _count(1 if mark is None else 2)
 
 
 _define("segment_pool_fwd_(Tensor emb, Tensor pos, int mode, Tensor(a!) out, Tensor(b!) cnt, Tensor(c!)? argmax) -> ()",
         _pool_fwd_)
-_define("segment_pool_bwd_(Tensor dout, Tensor pos, int mode, Tensor cnt, Tensor? argmax, Tensor(a!) demb) -> ()",
-        _pool_bwd_)
+_define("segment_pool_bwd_(Tensor dout, Tensor pos, int mode, Tensor cnt, Tensor? argmax, Tensor(a!) demb, "
+        "Tensor(b!)? mark) -> ()", _pool_bwd_)
 
 
 def _pool_batch_fwd_(x, batch, n_seg, mode, out, cnt, argmax):
@@ -514,6 +516,31 @@ def build_csr(edge_index: torch.Tensor, edge_weight: torch.Tensor, n_node: int, 
     return CSRAdj(n_node, rowptr, col, val, rowptr_t, col_t, val_t, deg, aggr).make_plans()
 
 
+def to_undirected(edge_index: torch.Tensor, edge_weight: torch.Tensor, n_node: int):
+    """Device-side PyG `to_undirected` (reference datasets.py:68-71): (edge_index, edge_weight) symmetrised, sorted by
+    (row, col), duplicate weights added; an input that already is undirected and duplicate-free comes back as is."""
+    lib = _lib.load()
+    ei = _req(edge_index, torch.int64, "edge_index", 2)
+    ew = _req(edge_weight, torch.float32, "edge_weight", 1)
+    nnz, dev = ei.shape[1], ei.device
+    if nnz == 0:
+        return ei, ew
+    with torch.cuda.device(dev):
+        ws_bytes = lib.glass_to_undirected_workspace_bytes(nnz)
+        if ws_bytes == 0:
+            check(-1, "to_undirected_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out_i = torch.empty((2, 2 * nnz), dtype=torch.int64, device=dev)
+        out_w = torch.empty(2 * nnz, dtype=torch.float32, device=dev)
+        m, already = C.c_int64(0), C.c_int(0)
+        check(lib.glass_to_undirected(_p(ei), _p(ew), nnz, n_node, _p(out_i), _p(out_w), C.byref(m), C.byref(already),
+                                      _p(ws), ws_bytes, _stream()), "to_undirected")
+        _count(6)
+    if already.value:
+        return ei, ew
+    return out_i[:, :m.value].contiguous(), out_w[:m.value].contiguous()
+
+
 # ---------------------------------------------------------------------------------------------
 # autograd building blocks
 # ---------------------------------------------------------------------------------------------
@@ -672,10 +699,13 @@ def _injected_keep(n, c):
 
 
 _rng_states = {}
+_rng_seed = None        # set by manual_seed(); devices whose state does not exist yet start from it
 
 
 def manual_seed(seed: int) -> None:
     """Re-seed the in-kernel dropout generator of every device (counter back to 0)."""
+    global _rng_seed
+    _rng_seed = seed & ((1 << 63) - 1)
     for t in _rng_states.values():
         t.copy_(torch.tensor([seed & ((1 << 63) - 1), 0, 0, 0], dtype=torch.int64))
 
@@ -687,7 +717,7 @@ def _rng_state(device) -> torch.Tensor:
     key = (device.type, device.index)
     t = _rng_states.get(key)
     if t is None:
-        seed = int(torch.initial_seed()) & ((1 << 63) - 1)
+        seed = _rng_seed if _rng_seed is not None else int(torch.initial_seed()) & ((1 << 63) - 1)
         t = _rng_states[key] = torch.tensor([seed, 0, 0, 0], dtype=torch.int64, device=device)
     return t
 
@@ -731,7 +761,22 @@ def register_grad_buffer(param: torch.Tensor, buffer: torch.Tensor) -> None:
     data-parallel exchange (glass_b200/dp.py) wants its gradient in peer-visible memory without a 14.7 MB copy."""
     if buffer.shape != param.shape or not buffer.is_contiguous() or buffer.dtype != param.dtype:
         raise ValueError("gradient buffer must match the parameter (shape, dtype, contiguous)")
-    _grad_sinks[param.data_ptr()] = buffer
+    import weakref
+    for k in [k for k, (ref, _) in _grad_sinks.items() if ref() is None]:      # parameters that no longer exist
+        del _grad_sinks[k]
+    _grad_sinks[param.data_ptr()] = (weakref.ref(param), buffer)
+
+
+def _grad_sink_for(x: torch.Tensor):
+    """The registered gradient buffer of `x`, only while the parameter it was registered for is alive and still owns
+    that address (a freed parameter's address is recycled by the caching allocator)."""
+    hit = _grad_sinks.get(x.data_ptr())
+    if hit is None:
+        return None
+    param, sink = hit[0](), hit[1]
+    if param is None or param.data_ptr() != x.data_ptr() or param.shape != x.shape or sink.device != x.device:
+        return None
+    return sink
 
 
 class _GraphNorm(torch.autograd.Function):
@@ -756,8 +801,8 @@ class _GraphNorm(torch.autograd.Function):
         act, drop_p = ctx.cfg
         dout, _ = _rowmajor(dout)
         n, c = x.shape
-        sink = _grad_sinks.get(x.data_ptr())
-        if sink is not None and sink.shape == x.shape and sink.device == x.device:
+        sink = _grad_sink_for(x)
+        if sink is not None:
             dx = sink.view(sink.shape)      # a fresh alias: autograd adopts it as .grad without cloning
         else:
             dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
@@ -834,15 +879,18 @@ def _validate_ids(ids: torch.Tensor, rows: int, what: str) -> None:
     node-id tensor of a dataset never changes) and skipped while a CUDA graph is being captured."""
     if ids.numel() == 0 or torch.cuda.is_current_stream_capturing():
         return
+    import weakref
+    base = ids._base if ids._base is not None else ids
     key = (ids.data_ptr(), ids._version, ids.numel(), str(ids.device), rows)
-    if key in _ids_checked:
+    hit = _ids_checked.get(key)
+    if hit is not None and hit() is base:       # the same live tensor (not another one at a recycled address)
         return
     lo, hi = int(ids.min()), int(ids.max())
     if lo < 0 or hi >= rows:
         raise IndexError(f"{what}: index out of range [0, {rows}) (min {lo}, max {hi})")
     if len(_ids_checked) > 64:
         _ids_checked.clear()
-    _ids_checked[key] = True
+    _ids_checked[key] = weakref.ref(base)
 
 
 class _SpMMGraphNorm(torch.autograd.Function):
@@ -887,23 +935,28 @@ class _SpMMGraphNorm(torch.autograd.Function):
 
 def spmm_graph_norm(adj: CSRAdj, x, weight, bias, mean_scale, eps: float = 1e-5, act: int = ACT_NONE, p: float = 0.0,
                     training: bool = False):
-    if adj.n == 0 or x.shape[0] == 0:
+    # the statistics-in-the-epilogue form pays where GraphNorm would otherwise take three launches; tiny matrices
+    # (cluster kernel) and large power-of-two widths (cooperative kernel) are already one launch
+    if adj.n == 0 or x.shape[0] == 0 or _lib.load().glass_graphnorm_launches(adj.n, x.shape[1]) == 1:
         return graph_norm(spmm(adj, x), weight, bias, mean_scale, eps, act, p, training)
     return _SpMMGraphNorm.apply(x, adj, weight, bias, mean_scale, eps, act, p, training)
 
 
 def conv_fusable(k_in: int, h: int, path: Optional[int] = None) -> bool:
-    """True when one GLASSConv layer (in width k_in, out width h) can run as the fused chain below: the
-    tcgen05 kernels with operands normalised on load (glass_pair_norm_operand_supported)."""
+    """True when one GLASSConv layer (in width k_in, out width h) can run as the single autograd node below (the
+    tcgen05 kernels incl. the dW kernel: needed for the accumulate-into-dX epilogue and the normalised loaders)."""
     path = _gemm_path if path is None else path
-    if path == GEMM_SIMT or not _conv_fused:
+    if path == GEMM_SIMT:
         return False
     lib = _lib.load()
     return bool(lib.glass_pair_norm_operand_supported(k_in, 0, h)) and bool(lib.glass_pair_norm_operand_supported(h, k_in, h))
 
 
 class _GlassConv(torch.autograd.Function):
-    """One GLASSConv layer (impl/models.py:153-174) as FOUR kernels forward:
+    """One GLASSConv layer (impl/models.py:153-174) as ONE autograd node.  Default (fuse_norm False): pair GEMM, SpMM,
+    one-launch GraphNorm + dropout, pair GEMM forward; backward = comb dX / dW, one-launch GraphNorm backward, A^T
+    SpMM, trans dX / dW where the trans dX epilogue ACCUMULATES into the x_ gradient the comb GEMM wrote (x_ feeds both
+    GEMMs; no separate add pass).  With fuse_norm (GLASS_B200_CONV_FUSED=1) the layer is FOUR kernels forward:
         pair GEMM (trans_fns + activation + label mix)                                         :158-162
         SpMM whose epilogue also emits the GraphNorm column sums                               :164-165
         finalize (normalisation constants + this call's dropout bits)
@@ -915,7 +968,7 @@ class _GlassConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_, adj, tw0, tb0, tw1, tb1, gw, gb, gms, cw0, cb0, cw1, cb1, mask, z_ratio, act, eps, p,
-                training, path):
+                training, path, fuse_norm):
         x_, _ = _rowmajor(_req(x_, torch.float32, "x_", 2))
         mask = _req(mask, torch.uint8, "mask", 1)
         n, k_in = x_.shape
@@ -929,25 +982,34 @@ class _GlassConv(torch.autograd.Function):
         xm = torch.empty((n, h), **f32)
         acts = torch.empty((n, 2 * h), **f32) if (need_grad and act != ACT_NONE) else None
         _ops.pair_linear_mix_fwd_(x_, None, tw0, tb0, tw1, tb1, mask, float(z_ratio), act, path, xm, acts)
-        # :164 with the statistics of :165
         y = torch.empty((n, h), **f32)
-        partial = _stats_table(h, dev)
-        nblk = _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, xm, y, partial)
         drop_p, keep, rng, bits = _dropout_source(n, h, p, training, dev)
         stats = torch.empty((6, h), **f32)
-        _ops.graphnorm_stats_(partial, nblk, n, gw, gb, gms, float(eps), keep, drop_p, rng, bits, stats)
-        # :165-173
         out = torch.empty((n, h), **f32)
-        _ops.pair_linear_mix_fwd_ex_(y, x_, cw0, cb0, cw1, cb1, mask, float(z_ratio), ACT_NONE, path, out, None,
-                                     stats, bits, drop_p, ACT_NONE, None, None, 0.0, ACT_NONE)
-        ctx.save_for_backward(x_, acts, y, stats, keep, rng, bits, mask, tw0, tw1, gw, gms, cw0, cw1)
-        ctx.adj, ctx.cfg = adj, (float(z_ratio), act, drop_p, path)
+        g = None
+        if fuse_norm:
+            # :164 with the statistics of :165 in the SpMM epilogue; :165-173 with the norm applied by the GEMM loader
+            partial = _stats_table(h, dev)
+            nblk = _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, xm, y, partial)
+            _ops.graphnorm_stats_(partial, nblk, n, gw, gb, gms, float(eps), keep, drop_p, rng, bits, stats)
+            _ops.pair_linear_mix_fwd_ex_(y, x_, cw0, cb0, cw1, cb1, mask, float(z_ratio), ACT_NONE, path, out, None,
+                                         stats, bits, drop_p, ACT_NONE, None, None, 0.0, ACT_NONE)
+        else:
+            # :164, then GraphNorm + dropout as ONE launch that writes the normalised matrix (measured faster than
+            # the loader fusion: the tcgen05 kernels are bound by their CUDA-core warps)
+            _run_spmm(adj.rowptr, adj.col, adj.val, adj.plan, xm, y)
+            g = torch.empty((n, h), **f32)
+            _ops.graphnorm_fwd_(y, gw, gb, gms, float(eps), ACT_NONE, keep, drop_p, rng, bits, g, stats,
+                                _gn_workspace(n, h, dev))
+            _ops.pair_linear_mix_fwd_(g, x_, cw0, cb0, cw1, cb1, mask, float(z_ratio), ACT_NONE, path, out, None)
+        ctx.save_for_backward(x_, acts, y, stats, keep, rng, bits, mask, tw0, tw1, gw, gms, cw0, cw1, g)
+        ctx.adj, ctx.cfg = adj, (float(z_ratio), act, drop_p, path, fuse_norm)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x_, acts, y, stats, keep, rng, bits, mask, tw0, tw1, gw, gms, cw0, cw1 = ctx.saved_tensors
-        z_ratio, act, drop_p, path = ctx.cfg
+        x_, acts, y, stats, keep, rng, bits, mask, tw0, tw1, gw, gms, cw0, cw1, g = ctx.saved_tensors
+        z_ratio, act, drop_p, path, fuse_norm = ctx.cfg
         adj = ctx.adj
         dout, _ = _rowmajor(dout)
         n, k_in = x_.shape
@@ -962,8 +1024,12 @@ class _GlassConv(torch.autograd.Function):
         dcw0, dcw1 = torch.empty_like(cw0), torch.empty_like(cw1)
         dcb0, dcb1 = torch.empty(h, **f32), torch.empty(h, **f32)
         ws = torch.empty(lib.glass_pair_linear_mix_bwd_workspace_bytes(n, h, h + k_in), dtype=torch.uint8, device=dev)
-        _ops.pair_linear_mix_bwd_ex_(dout, None, y, x_, cw0, cw1, mask, z_ratio, ACT_NONE, path, dg, dx_, dcw0, dcb0,
-                                     dcw1, dcb1, ws, stats, bits, drop_p, ACT_NONE, None, None, 0.0, ACT_NONE, 0, 0)
+        if fuse_norm:
+            _ops.pair_linear_mix_bwd_ex_(dout, None, y, x_, cw0, cw1, mask, z_ratio, ACT_NONE, path, dg, dx_, dcw0, dcb0,
+                                         dcw1, dcb1, ws, stats, bits, drop_p, ACT_NONE, None, None, 0.0, ACT_NONE, 0, 0)
+        else:
+            _ops.pair_linear_mix_bwd_(dout, None, g, x_, cw0, cw1, mask, z_ratio, ACT_NONE, path, dg, dx_, dcw0, dcb0,
+                                      dcw1, dcb1, ws)
         # GraphNorm + dropout backward, then A^T
         dy = torch.empty((n, h), **f32)
         dgw, dgb, dgms = torch.empty_like(gw), torch.empty_like(gw), torch.empty_like(gw)
@@ -979,7 +1045,7 @@ class _GlassConv(torch.autograd.Function):
                                      dtw1, dtb1, ws, None, None, 0.0, ACT_NONE, None, None, 0.0, ACT_NONE,
                                      1 if want_dx else 0, 0)
         return (dx_, None, dtw0, dtb0, dtw1, dtb1, dgw, dgb, dgms, dcw0, dcb0, dcw1, dcb1, None, None, None, None,
-                None, None, None)
+                None, None, None, None)
 
 
 def glass_conv(x_, adj: CSRAdj, trans, gn, comb, mask, z_ratio: float, act: int, p: float, training: bool,
@@ -987,7 +1053,7 @@ def glass_conv(x_, adj: CSRAdj, trans, gn, comb, mask, z_ratio: float, act: int,
     """Fused GLASSConv.forward; trans / comb = (w0, b0, w1, b1), gn = (weight, bias, mean_scale, eps)."""
     gw, gb, gms, eps = gn
     return _GlassConv.apply(x_, adj, *trans, gw, gb, gms, *comb, mask, z_ratio, act, eps, p, training,
-                            _gemm_path if path is None else path)
+                            _gemm_path if path is None else path, _conv_fused)
 
 
 def pair_linear_mix_into(a1, a2, w0, b0, w1, b1, mask, z_ratio: float, act: int, out, acts=None, path=None):
@@ -1022,6 +1088,39 @@ def glass_conv_from_base(adj: CSRAdj, x_, y_u, delta, mask, gn, comb, z_ratio: f
     return out
 
 
+_embed_plans = {}
+
+
+def _embed_plan(ids: torch.Tensor):
+    """Ordered-accumulation plan of an id tensor (init path, cached by address / version): stable sort by id, runs of
+    at most 128 sorted positions with one id, and for every distinct id its runs."""
+    import weakref
+    base = ids._base if ids._base is not None else ids          # the long-lived tensor the caller holds (x of the dataset)
+    key = (ids.data_ptr(), ids._version, ids.numel(), str(ids.device))
+    hit = _embed_plans.get(key)
+    if hit is not None and hit[0]() is base:                     # same live tensor, not a recycled address
+        return hit[1]
+    n = ids.numel()
+    sorted_ids, perm = torch.sort(ids, stable=True)
+    pos = torch.arange(n, device=ids.device)
+    change = torch.ones(n, dtype=torch.bool, device=ids.device)
+    if n > 1:
+        change[1:] = sorted_ids[1:] != sorted_ids[:-1]
+    seg_start = torch.cummax(torch.where(change, pos, torch.zeros_like(pos)), 0).values
+    run_start = change | ((pos - seg_start) % 128 == 0)
+    run_begin = torch.nonzero(run_start).flatten()
+    run_end = torch.cat((run_begin[1:], torch.tensor([n], device=ids.device)))
+    run_id = sorted_ids[run_begin]
+    uid, counts = torch.unique_consecutive(run_id, return_counts=True)
+    first = torch.cumsum(counts, 0) - counts
+    plan = dict(perm=perm.contiguous(), run_begin=run_begin.to(torch.int32), run_end=run_end.to(torch.int32),
+                uid=uid.contiguous(), first=first.to(torch.int32), runs=counts.to(torch.int32))
+    if len(_embed_plans) > 16:
+        _embed_plans.clear()
+    _embed_plans[key] = (weakref.ref(base), plan)
+    return plan
+
+
 class _Embedding(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, table):
@@ -1032,14 +1131,26 @@ class _Embedding(torch.autograd.Function):
         _ops.embedding_fwd_(table, ids, out)
         ctx.save_for_backward(ids)
         ctx.rows = table.shape[0]
+        ctx.plan = None if torch.cuda.is_current_stream_capturing() else _embed_plan(ids)   # built outside any capture
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (ids,) = ctx.saved_tensors
         dout, _ = _rowmajor(dout)
-        dtable = torch.zeros((ctx.rows, dout.shape[1]), dtype=torch.float32, device=dout.device)
-        _ops.embedding_bwd_(dout, ids, dtable)
+        h = dout.shape[1]
+        dtable = torch.zeros((ctx.rows, h), dtype=torch.float32, device=dout.device)
+        plan = ctx.plan
+        if plan is None:                  # first use happened under capture: atomics (not bit-reproducible)
+            _ops.embedding_bwd_(dout, ids, dtable)
+            return None, dtable
+        lib = _lib.load()
+        run_sum = torch.empty((plan["run_begin"].numel(), h), dtype=torch.float32, device=dout.device)
+        check(lib.glass_embedding_bwd_ordered(_p(dout), dout.stride(0), _p(plan["perm"]), _p(plan["run_begin"]),
+                                              _p(plan["run_end"]), plan["run_begin"].numel(), _p(plan["uid"]),
+                                              _p(plan["first"]), _p(plan["runs"]), plan["uid"].numel(), _p(run_sum),
+                                              _p(dtable), ctx.rows, h, _stream()), "embedding_bwd_ordered")
+        _count(2)
         return None, dtable
 
 
@@ -1067,8 +1178,11 @@ class _SegmentPool(torch.autograd.Function):
         pos, cnt, argmax = ctx.saved_tensors
         mode, n = ctx.cfg
         dout, _ = _rowmajor(dout)
-        demb = torch.zeros((n, dout.shape[1]), dtype=torch.float32, device=dout.device)
-        _ops.segment_pool_bwd_(dout, pos, mode, cnt, argmax, demb)
+        # node-centric ordered kernel: every row of demb is written (no zero-fill), additions in subgraph order
+        demb = torch.empty((n, dout.shape[1]), dtype=torch.float32, device=dout.device)
+        mark = torch.empty(_lib.load().glass_segment_pool_bwd_scratch_bytes(pos.shape[0], n), dtype=torch.uint8,
+                           device=dout.device)
+        _ops.segment_pool_bwd_(dout, pos, mode, cnt, argmax, demb, mark)
         return demb, None, None
 
 

@@ -68,6 +68,17 @@ int glass_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t
                     int32_t* col_t, float* val_t, float* deg, int64_t* nnz_out_host, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* to_undirected on the device (reference datasets.py:68-71 -> PyG to_undirected + coalesce: the step that sorts
+ * and de-duplicates the edge list before it ever reaches buildAdj).  out_index int64 [2, 2*nnz] and out_w fp32
+ * [2*nnz] are capacities; rows of the result are out_index[0 .. m) and out_index[2*nnz .. 2*nnz + m) with
+ * m = *nnz_out_host, sorted by (row, col), duplicate weights added in input order.  *already_host = 1 when the
+ * input already was undirected and duplicate-free (the reference leaves such a graph untouched).  Init path: one
+ * host synchronisation. */
+size_t glass_to_undirected_workspace_bytes(int64_t nnz);
+int glass_to_undirected(const int64_t* edge_index, const float* edge_weight, int64_t nnz, int64_t n_node,
+                        int64_t* out_index, float* out_w, int64_t* nnz_out_host, int* already_host,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * adj @ x  (impl/models.py:164; backward = the same kernel on the transposed CSR)
  * y[r, :] = sum_{e in row r} val[e] * x[col[e], :]  (deterministic: fixed summation order per shape).
@@ -261,6 +272,15 @@ int glass_embedding_fwd(const float* table, const int64_t* ids, float* out, int6
                         int64_t rows, int h, void* stream);
 int glass_embedding_bwd(const float* dout, int64_t lddo, const int64_t* ids, float* dtable, int64_t n,
                         int64_t rows, int h, void* stream);
+/* Deterministic variant (bit-reproducible run to run): rows are added in the order of a stable sort by id.  Plan
+ * (built once per id tensor by the host layer): perm int64 [n] = stable argsort of ids; runs = stretches of at most
+ * 128 sorted positions holding ONE id (run_begin / run_end int32 [n_runs]); for every distinct id uid[u] its first
+ * run and run count.  run_sum [n_runs, h] is scratch.  Rows of dtable whose id does not occur are NOT written
+ * (caller zero-fills). */
+int glass_embedding_bwd_ordered(const float* dout, int64_t lddo, const int64_t* perm, const int32_t* run_begin,
+                                const int32_t* run_end, int64_t n_runs, const int64_t* uid,
+                                const int32_t* uid_first_run, const int32_t* uid_runs, int64_t n_uid,
+                                float* run_sum, float* dtable, int64_t rows, int h, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Padded-subgraph pooling (GLASS.Pool impl/models.py:346-350 = pad2batch + emb[pos] + pool_fn;
@@ -268,14 +288,19 @@ int glass_embedding_bwd(const float* dout, int64_t lddo, const int64_t* ids, flo
  * the padded row directly; row lanes accumulate strided rows in pad order and are combined in a
  * fixed order (deterministic).  out [b, d]; cnt fp32 [b] (valid nodes per row); argmax int32 [b, d] (MAX only,
  * else may be NULL): node id of the first maximum, -1 for an empty row.
- * bwd ACCUMULATES into demb [n_node, d] (caller zero-fills) with atomics.
+ * bwd, scratch == NULL: ACCUMULATES into demb [n_node, d] (caller zero-fills) with atomics (order of the
+ *   additions for a node that occurs in several subgraphs is not reproducible);
+ * bwd, scratch != NULL (glass_segment_pool_bwd_scratch_bytes(b, n_node) bytes): deterministic -- WRITES every row
+ *   of demb (zeros outside the batch); per-subgraph membership bitmaps are built first, then a node's contributions
+ *   are added in ascending subgraph order by one thread per column.
  * ------------------------------------------------------------------------------------------ */
 int glass_segment_pool_fwd(const float* emb, int64_t lde, const int64_t* pos, int64_t b, int64_t lmax,
                            int mode, float* out, int64_t ldo, float* cnt, int32_t* argmax, int d,
                            int64_t n_node, void* stream);
 int glass_segment_pool_bwd(const float* dout, int64_t lddo, const int64_t* pos, int64_t b, int64_t lmax,
                            int mode, const float* cnt, const int32_t* argmax, float* demb, int64_t ldde,
-                           int d, int64_t n_node, void* stream);
+                           int d, int64_t n_node, void* scratch, size_t scratch_bytes, void* stream);
+size_t glass_segment_pool_bwd_scratch_bytes(int64_t b, int64_t n_node);
 /* PoolModule.forward(x, batch) (impl/models.py:287-292): x [m, d] rows already gathered,
  * batch int64 [m] sorted ascending (as pad2batch produces). */
 int glass_segment_pool_batch_fwd(const float* x, int64_t ldx, const int64_t* batch, int64_t m, int64_t n_seg,

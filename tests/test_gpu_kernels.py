@@ -485,3 +485,30 @@ def test_fused_adam_matches_torch_adam():
     p_new[2].grad = None
     new.step()
     assert torch.equal(p_new[2].detach(), before[2]) and not torch.equal(p_new[0].detach(), before[0])
+
+
+# ------------------------------------------------------------------------------------------ to_undirected (device)
+def test_to_undirected_on_device_matches_host_coalesce():
+    """ops.to_undirected == PyG to_undirected + coalesce (datasets.coalesce_undirected restates it on the host and is
+    pinned against the reference's loader in tests/test_host_logic.py): directed, duplicated, self-loop input;
+    an already undirected list comes back untouched."""
+    from glass_b200 import datasets, ops
+    g = torch.Generator().manual_seed(3)
+    n = 500
+    e = torch.randint(0, n, (2, 4000), generator=g)
+    e[:, :50] = e[:, 50:100]                                    # duplicates
+    e[1, 100:120] = e[0, 100:120]                               # self loops
+    w = torch.rand(e.shape[1], generator=g) + 0.5
+    ref_i, ref_w = datasets.coalesce_undirected(e, w, n)
+    got_i, got_w = ops.to_undirected(e.to(DEV), w.to(DEV), n)
+    assert torch.equal(got_i.cpu(), ref_i)
+    assert rel_err(got_w.cpu(), ref_w) < 1e-6
+    again_i, again_w = ops.to_undirected(got_i, got_w, n)       # idempotent on an undirected, coalesced list
+    assert again_i.data_ptr() == got_i.data_ptr() and torch.equal(again_w, got_w)
+    dup = torch.tensor([[0, 0], [1, 1]], device=DEV)            # a duplicated directed edge is NOT "already undirected"
+    di, dw = ops.to_undirected(dup, torch.ones(2, device=DEV), 4)
+    assert di.tolist() == [[0, 1], [1, 0]] and dw.tolist() == [2.0, 2.0]
+    # the graph container uses it when its tensors live on the GPU
+    bg = datasets.BaseGraph(torch.empty((n, 1, 0), device=DEV), e.to(DEV), w.to(DEV), torch.zeros((1, 1), dtype=torch.int64),
+                            torch.zeros(1), torch.zeros(1, dtype=torch.int64))
+    assert torch.equal(bg.edge_index.cpu(), ref_i)

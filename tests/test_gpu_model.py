@@ -385,8 +385,8 @@ def test_pretraining_modules_match_reference_golden():
     loss.backward()
     assert rel_err(logits.detach().cpu(), d["logits"]) < TOL
     assert abs(float(loss) - float(d["loss"])) < TOL
-    for k, p in m.named_parameters():
-        assert rel_err(p.grad.cpu(), d[f"grad.{k}"]) < TOL, k
+    errs = {k: rel_err(p.grad.cpu(), d[f"grad.{k}"]) for k, p in m.named_parameters()}
+    assert max(errs.values()) < TOL, {k: v for k, v in errs.items() if v >= TOL}
 
 
 # ------------------------------------------------------------------------------------------
@@ -457,3 +457,40 @@ def test_shared_base_unsupported_width_raises():
     x, ei, ew, pos, z = _dev(c)
     with pytest.raises(NotImplementedError):
         m.shared_base(x, ei, ew)
+
+
+@pytest.mark.parametrize("name", ["cutratio_like", "ppibp_like", "emuser_like", "component_like"])
+def test_seeded_training_is_bit_reproducible(name):
+    """SURVEY.md section 5 "Determinism": two runs from the same seed give bit-identical losses and parameters.
+    Pooling / embedding backward add in a fixed order (no float atomics), statistics are reduced in a fixed order,
+    the dropout generator is counter based."""
+    from glass_b200 import ops, utils
+    c = load_model_case(name)
+    x, ei, ew, pos, _ = _dev(c)
+    y = c["y"].to(DEV)
+    loss_fn = O.loss_fn_for(c["cfg"].out_dim == 1)
+    n = x.shape[0]
+    g = torch.Generator().manual_seed(11)
+    batches = []
+    for _ in range(4):
+        p = c["pos"].clone()
+        perm = torch.randperm(n, generator=g)
+        p[p >= 0] = perm[p[p >= 0]]
+        p[1] = p[0]                                   # the same nodes in two subgraphs: several gradients per node
+        batches.append(p.to(DEV))
+    runs = []
+    for _ in range(2):
+        m = _product_from_case(c, dropout=0.3).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+        ops.manual_seed(7)
+        losses = []
+        for p in batches:
+            opt.zero_grad()
+            loss = loss_fn(m(x, ei, ew, p, utils.MaxZOZ(x, p), id=0), y)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        runs.append((losses, {k: v.clone() for k, v in m.state_dict().items()}))
+    assert runs[0][0] == runs[1][0]
+    for k, v in runs[0][1].items():
+        assert torch.equal(v, runs[1][1][k]), k
