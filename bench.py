@@ -214,7 +214,32 @@ def spmm_roofline(adj, h: int, reps: int = 20):
                     traffic, traffic_note = t["dram_bytes_per_launch"], t.get("source", "")
     except Exception:
         pass
-    return {"bound": "hbm", "kernel": "k_spmm (glass_spmm_csr)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # second roofline: the kernel's real bound is the L2 -> SM gather stream (4 H nnz bytes; x is L2 resident).  The
+    # probe reads the same number of pseudo-random 4H-byte rows with the same lane layout, 8 loads in flight, no index
+    # stream and no dependent FMA chain: the gather rate this device can deliver to ANY kernel of this shape.
+    l2 = None
+    if h in (32, 64, 128) and adj.n * h < 2 ** 31:
+        import ctypes as C
+        from glass_b200 import _lib
+        lib = _lib.load()
+        sink = torch.empty(lib.glass_sm_count() * 5 * 256, device=dev)
+        probe = lambda: _lib.check(lib.glass_l2_gather_probe(C.c_void_p(x.data_ptr()), x.stride(0), adj.n, h, adj.nnz,
+                                                             C.c_void_p(sink.data_ptr()), sink.numel(),
+                                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "probe")
+        for _ in range(3):
+            probe()
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            probe()
+            b.record()
+        torch.cuda.synchronize()
+        pm = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+        gb = 4 * h * adj.nnz
+        l2 = {"probe_gbs": gb / (pm * 1e-3) / 1e9, "probe_us": pm * 1e3, "spmm_gbs": gb / (avg * 1e-3) / 1e9,
+              "frac": pm / avg, "what": "glass_l2_gather_probe: nnz pseudo-random 4H-byte row gathers from the same x "
+                                        "(L2 flushed before each launch); frac = k_spmm gather rate / probe gather rate"}
+    return {"bound": "hbm", "kernel": "k_spmm (glass_spmm_csr)", "achieved": achieved, "peak": peak, "unit": "GB/s", "l2_gather": l2,
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes": algo, "us_per_launch": avg * 1e3,
             "us_min": ms[0] * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
             "gather_bytes_l2": 4 * h * adj.nnz, "gather_gbs_l2": 4 * h * adj.nnz / (avg * 1e-3) / 1e9,
@@ -375,6 +400,8 @@ def run_product(args):
         line["e2e"] = {"value": e2e_value, "unit": "subgraphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "api": "glass_b200.graphed.train_epoch(GraphedTrainStep, pinned host batches), loss.item() every step"}
         line["cuda_graph"] = not args.no_graph
+        if world > 1:   # "symm": fused reduce-scatter + Adam + all-gather over NVLink peer memory; "nccl": all-reduce, then Adam
+            line["config"]["grad_exchange"] = step.dp_mode
         line["gpu_launches"] = launches
         line["clocks"] = clocks.summary()
         adj = model.conv.convs[0].adj

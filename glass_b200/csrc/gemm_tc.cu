@@ -28,10 +28,12 @@ namespace {
 
 constexpr int BM = 128;                 // rows per tile == UMMA M (TMEM lane == row)
 constexpr int KBF = 32;                 // floats per K-block == one 128-byte swizzle row
-constexpr int kEpiWarps = 8, kLoadWarps = 16;
-constexpr int kLoadThreads = kLoadWarps * 32;
-constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps) * 32;
-constexpr int kCPT = BM * 8 / kLoadThreads;   // 16-byte chunks per loader thread and K-block
+// 25 warps per CTA: EW epilogue warps, one MMA-issuing warp, 24 - EW operand-loader warps.  EW = 8 (16 loaders) where the
+// loader sets the pace (dX: it rebuilds dP from dOut / acts / mask), EW = 16 (8 loaders) where the epilogue does
+// (forward with saved activations: 9 K cycles per tile on 8 warps against 1.4 K cycles per K-block of the main loop).
+constexpr int kWorkWarps = 24;
+constexpr int kThreads = (kWorkWarps + 1) * 32;
+constexpr int kMaxEpiWarps = 16;
 constexpr int kStageBytes = BM * 128 * 2;   // hi + lo tile of one K-block
 constexpr int kMaxSmem = 232448;            // 227 KB opt-in limit per CTA
 
@@ -213,8 +215,12 @@ __device__ __forceinline__ void stamp(long long* dbg, int idx) {
 
 // ACT is a template parameter: with a run-time activation every element of the epilogue / the dP loader carried two
 // compare-and-branch pairs (the kernels are bound by the instruction count of their CUDA-core warps, not by memory).
-template <bool BWD, bool NORM, int ACT>
+template <bool BWD, bool NORM, int ACT, int EW>
 __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
+    constexpr int kEpiWarps = EW, kLoadWarps = kWorkWarps - EW, kLoadThreads = kLoadWarps * 32;
+    constexpr int kCPT = BM * 8 / kLoadThreads;      // 16-byte chunks per loader thread and K-block
+    constexpr int PARTS = EW / 4;                    // epilogue warps per TMEM lane quadrant: they split the columns
+    static_assert(EW % 4 == 0 && (BM * 8) % kLoadThreads == 0, "warp split");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             const int acc = it & 1;
             mbar_wait(smem_u32(tfull + acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int quad = warp & 3, half = warp >> 2;         // TMEM lane quadrant (== warp % 4), column half
+            const int quad = warp & 3, half = warp >> 2;         // TMEM lane quadrant (== warp % 4), column part
             const int64_t row = tile * RT + quad * 32 + lane;
             const bool row_ok = row < P.n && quad * 32 + lane < RT;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N);
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     c0 = lab ? 1.f - P.z : P.z;
                 }
                 if (P.staged) {
-                    const int c_lo = half * (H >> 1), c_hi = c_lo + (H >> 1);
+                    const int c_lo = half * (H / PARTS), c_hi = c_lo + (H / PARTS);
                     for (int cb = c_lo; cb < c_hi; cb += 16) {
                         float p0[16], p1[16];
                         tmem_ld16(t_row + (uint32_t)cb, p0);
@@ -385,9 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     tmem_ld8(t_row + (uint32_t)(half * 8), n0);
                     tmem_ld8(t_row + (uint32_t)(H + half * 8), n1);
                 }
-                for (int c = half * 8; c < H; c += 16) {
-                    const bool dbg_on = P.dbg && threadIdx.x == 0 && it == 1 && c < 32;     // CTA 0 / warp 0, second tile
-                    if (dbg_on) stamp(P.dbg, 210 + (c >> 4) * 4);
+                for (int c = half * 8; c < H; c += PARTS * 8) {
+                    const bool dbg_on = P.dbg && threadIdx.x == 0 && it == 1 && c < 2 * PARTS * 8;     // CTA 0 / warp 0, second tile
+                    if (dbg_on) stamp(P.dbg, 210 + (c / (PARTS * 8)) * 4);
                     const float4 ba0 = ldg_f4(P.b0 + c), ba1 = ldg_f4(P.b0 + c + 4);   // biases: 512 B, L1 resident
                     const float4 bb0 = ldg_f4(P.b1 + c), bb1 = ldg_f4(P.b1 + c + 4);
                     const float bA[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
@@ -396,15 +402,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                     float p0[8], p1[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) p0[u] = n0[u], p1[u] = n1[u];
-                    if (c + 16 < H) {
-                        tmem_ld8(t_row + (uint32_t)(c + 16), n0);
-                        tmem_ld8(t_row + (uint32_t)(H + c + 16), n1);
+                    if (c + PARTS * 8 < H) {
+                        tmem_ld8(t_row + (uint32_t)(c + PARTS * 8), n0);
+                        tmem_ld8(t_row + (uint32_t)(H + c + PARTS * 8), n1);
                     } else {                        // last TMEM read of this tile: hand the accumulator back now
                         tc_fence_before();
                         mbar_arrive(smem_u32(tempty + acc));
                         released = true;
                     }
-                    if (dbg_on) stamp(P.dbg, 211 + (c >> 4) * 4);
+                    if (dbg_on) stamp(P.dbg, 211 + (c / (PARTS * 8)) * 4);
                     if (row_ok) {
                         float o[8];
 #pragma unroll
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                             p1[u] = act_fwd(p1[u] + bB[u], ACT);
                             o[u] = __fadd_rn(__fmul_rn(c1, p1[u]), __fmul_rn(c0, p0[u]));
                         }
-                        if (dbg_on) stamp(P.dbg, 212 + (c >> 4) * 4);
+                        if (dbg_on) stamp(P.dbg, 212 + (c / (PARTS * 8)) * 4);
                         if (P.wide) {
                             st_global_256(P.out + row * P.ldo + c, o);
                             if (P.acts) {
@@ -433,12 +439,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
                                 pb[1] = make_float4(p1[4], p1[5], p1[6], p1[7]);
                             }
                         }
-                        if (dbg_on) stamp(P.dbg, 213 + (c >> 4) * 4);
+                        if (dbg_on) stamp(P.dbg, 213 + (c / (PARTS * 8)) * 4);
                     }
                 }
                 }
             } else if (P.staged) {
-                const int c_lo = half * (N >> 1), c_hi = c_lo + (N >> 1);
+                const int c_lo = half * (N / PARTS), c_hi = c_lo + (N / PARTS);
                 for (int cb = c_lo; cb < c_hi; cb += 16) {
                     float d[16];
                     tmem_ld16(t_row + (uint32_t)cb, d);
@@ -478,13 +484,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
             } else {
                 float nd[8];
                 if (half * 8 < N) tmem_ld8(t_row + (uint32_t)(half * 8), nd);
-                for (int c = half * 8; c < N; c += 16) {
+                for (int c = half * 8; c < N; c += PARTS * 8) {
                     tmem_ld_wait();
                     float d[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) d[u] = nd[u];
-                    if (c + 16 < N) {
-                        tmem_ld8(t_row + (uint32_t)(c + 16), nd);
+                    if (c + PARTS * 8 < N) {
+                        tmem_ld8(t_row + (uint32_t)(c + PARTS * 8), nd);
                     } else {
                         tc_fence_before();
                         mbar_arrive(smem_u32(tempty + acc));
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pair_tc(const TcParams P) {
         const int lt = threadIdx.x - (kEpiWarps + 1) * 32;                 // 0 .. kLoadThreads-1
         const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t total = my_tiles * nkb;                              // K-blocks this CTA streams
-        constexpr int D = BWD ? 2 : 4;                                     // register ring depth (K-blocks in flight)
+        constexpr int D = (BWD || kCPT > 2) ? 2 : 4;                       // register ring depth (K-blocks in flight)
         struct Raw {
             float4 g[kCPT];
             float4 a[BWD ? kCPT : 1];
@@ -999,13 +1005,13 @@ __global__ void __launch_bounds__(256) k_pair_dw_tc_reduce(const float* __restri
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // shared-memory plan; returns false when the shape does not fit
-bool plan(int kdim, int ndim, bool norm, int stage_arrays, int* stages, size_t* bytes, uint32_t* tmem_cols) {
+bool plan(int kdim, int ndim, bool norm, int stage_arrays, int epi_warps, int* stages, size_t* bytes, uint32_t* tmem_cols) {
     if (ndim < 16 || ndim > 256 || ndim % 16 || kdim < 8 || kdim % 8 || kdim > 512) return false;
     const int nkb = (kdim + KBF - 1) / KBF;
     const size_t b = (size_t)2 * nkb * ndim * 128;
     const size_t fixed = b + 1024 /*alignment slack*/ + 256 /*barriers, TMEM slot*/ +
                          (norm ? (size_t)3 * kdim * sizeof(float) : 0) /*operand normalisation constants*/ +
-                         (size_t)stage_arrays * kEpiWarps * 512 * sizeof(float) /*staged epilogue tiles*/;
+                         (size_t)stage_arrays * epi_warps * 512 * sizeof(float) /*staged epilogue tiles*/;
     if (fixed + 2 * (size_t)kStageBytes > (size_t)kMaxSmem) return false;
     int s = (int)(((size_t)kMaxSmem - fixed) / kStageBytes);
     if (s > 6) s = 6;
@@ -1018,19 +1024,35 @@ bool plan(int kdim, int ndim, bool norm, int stage_arrays, int* stages, size_t* 
     return true;
 }
 
-template <bool BWD, bool NORM, int ACT>
+template <bool BWD, bool NORM, int ACT, int EW>
 int launch_act(TcParams& P, cudaStream_t st);
+
+// Epilogue warps of the forward kernel: 16 when the epilogue sets the pace (saved activations: three output arrays and
+// the activation math per tile), else 8.  GLASS_B200_TC_EPI=8|16 overrides (measurements).
+inline int fwd_epi_warps(const TcParams& P) {
+    static const int force = [] {
+        const char* e = getenv("GLASS_B200_TC_EPI");
+        return e ? atoi(e) : 0;
+    }();
+    if (force == 8 || force == 16) return force;
+    return (P.h % 32 == 0) ? 16 : 8;
+}
 
 template <bool BWD, bool NORM>
 int launch(TcParams& P, cudaStream_t st) {
     // backward without saved activations behaves like ACT_NONE (the activation derivative is 1)
     const int act = (BWD && !P.acts) ? GLASS_ACT_NONE : P.act;
-    if (act == GLASS_ACT_ELU) return launch_act<BWD, NORM, GLASS_ACT_ELU>(P, st);
-    if (act == GLASS_ACT_RELU) return launch_act<BWD, NORM, GLASS_ACT_RELU>(P, st);
-    return launch_act<BWD, NORM, GLASS_ACT_NONE>(P, st);
+    if (!BWD && fwd_epi_warps(P) == 16) {
+        if (act == GLASS_ACT_ELU) return launch_act<BWD, NORM, GLASS_ACT_ELU, BWD ? 8 : 16>(P, st);
+        if (act == GLASS_ACT_RELU) return launch_act<BWD, NORM, GLASS_ACT_RELU, BWD ? 8 : 16>(P, st);
+        return launch_act<BWD, NORM, GLASS_ACT_NONE, BWD ? 8 : 16>(P, st);
+    }
+    if (act == GLASS_ACT_ELU) return launch_act<BWD, NORM, GLASS_ACT_ELU, 8>(P, st);
+    if (act == GLASS_ACT_RELU) return launch_act<BWD, NORM, GLASS_ACT_RELU, 8>(P, st);
+    return launch_act<BWD, NORM, GLASS_ACT_NONE, 8>(P, st);
 }
 
-template <bool BWD, bool NORM, int ACT>
+template <bool BWD, bool NORM, int ACT, int EW>
 int launch_act(TcParams& P, cudaStream_t st) {
     size_t bytes = 0;
     // staged epilogue: output width (forward: h, backward: k1 + k2 with the a1|a2 boundary on a 16-column block)
@@ -1038,19 +1060,19 @@ int launch_act(TcParams& P, cudaStream_t st) {
     // (measured: no faster than the direct stores -- the epilogue is not bound by its store pattern -- so it is
     // opt-in, kept for experiments: GLASS_B200_TC_STAGED=1)
     static const bool want_stage = getenv("GLASS_B200_TC_STAGED") != nullptr;
-    P.staged = want_stage && (out_w % 32 == 0) && (!BWD || P.k1 % 16 == 0);
+    P.staged = want_stage && (out_w % (16 * (EW / 4)) == 0) && (!BWD || P.k1 % 16 == 0);
     int stage_arrays = P.staged ? ((!BWD && P.acts) ? 3 : 1) : 0;
-    if (P.staged && (!plan(P.kdim, P.ndim, NORM, stage_arrays, &P.stages, &bytes, &P.tmem_cols) || P.stages < 2)) {
+    if (P.staged && (!plan(P.kdim, P.ndim, NORM, stage_arrays, EW, &P.stages, &bytes, &P.tmem_cols) || P.stages < 2)) {
         P.staged = 0;
         stage_arrays = 0;
     }
-    if (!plan(P.kdim, P.ndim, NORM, stage_arrays, &P.stages, &bytes, &P.tmem_cols)) {
+    if (!plan(P.kdim, P.ndim, NORM, stage_arrays, EW, &P.stages, &bytes, &P.tmem_cols)) {
         set_error("pair_linear_mix (tcgen05): shape k=%d n=%d does not fit", P.kdim, P.ndim);
         return GLASS_ERR_UNSUPPORTED;
     }
     static bool attr_done = false;
     if (!attr_done) {
-        GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD, NORM, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        GLASS_CUDA(cudaFuncSetAttribute(k_pair_tc<BWD, NORM, ACT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_done = true;
     }
     // equal work per CTA: with 128-row tiles 57,333 rows are 448 tiles = 3.03 per SM, i.e. four rounds for a
@@ -1071,15 +1093,15 @@ int launch_act(TcParams& P, cudaStream_t st) {
         GLASS_CUDA(cudaMemset(dbg, 0, 256 * sizeof(long long)));
         P.dbg = dbg;
     }
-    k_pair_tc<BWD, NORM, ACT><<<grid, kThreads, bytes, st>>>(P);
+    k_pair_tc<BWD, NORM, ACT, EW><<<grid, kThreads, bytes, st>>>(P);
     GLASS_LAUNCH_CHECK();
     if (timeline) {   // debugging aid only: synchronises and prints CTA 0's event times in SM cycles
         long long h[256];
         GLASS_CUDA(cudaStreamSynchronize(st));
         GLASS_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(dbg);
-        fprintf(stderr, "[tc timeline bwd=%d k=%d n=%d rt=%d stages=%d] setup %lld end %lld\n  loader:", (int)BWD, P.kdim,
-                P.ndim, P.rows_per_tile, P.stages, h[1] - h[0], h[200] - h[0]);
+        fprintf(stderr, "[tc timeline bwd=%d k=%d n=%d rt=%d stages=%d epi_warps=%d] setup %lld end %lld\n  loader:", (int)BWD, P.kdim,
+                P.ndim, P.rows_per_tile, P.stages, EW, h[1] - h[0], h[200] - h[0]);
         for (int i = 0; i < 64 && h[16 + i]; ++i) fprintf(stderr, " %lld", h[16 + i] - h[0]);
         fprintf(stderr, "\n  mma:");
         for (int i = 0; i < 64 && h[80 + i]; ++i) fprintf(stderr, " %lld", h[80 + i] - h[0]);
@@ -1103,7 +1125,7 @@ bool pair_tc_supported(int k1, int k2, int h, int64_t lda1, int64_t lda2, const 
     int s;
     size_t b;
     uint32_t c;
-    return plan(k1 + k2, 2 * h, false, 0, &s, &b, &c) && plan(2 * h, k1 + k2, false, 0, &s, &b, &c);
+    return plan(k1 + k2, 2 * h, false, 0, 8, &s, &b, &c) && plan(2 * h, k1 + k2, false, 0, 8, &s, &b, &c);
 }
 
 static NormOp norm_op(const glass_norm_operand* n) {
@@ -1131,7 +1153,7 @@ bool pair_tc_norm_supported(int k1, int k2, int h) {
     int s;
     size_t b;
     uint32_t c;
-    return plan(K, 2 * h, true, 0, &s, &b, &c) && s >= 2;
+    return plan(K, 2 * h, true, 0, 8, &s, &b, &c) && s >= 2;
 }
 
 int pair_fwd_tc(const float* a1, int64_t lda1, int k1, const float* a2, int64_t lda2, int k2, const float* w0,

@@ -64,6 +64,7 @@ struct RowWork {
     const int32_t* rowptr;
     float* y;
     int64_t ldy;
+    int accumulate;            // y += A x instead of y = A x (column-partitioned phases of one product)
     __device__ __forceinline__ bool get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
         b = __ldg(rowptr + item);
         e = __ldg(rowptr + item + 1);
@@ -80,6 +81,7 @@ struct PlanWork {
     int64_t ldy;
     float* scratch;            // [n_slots, ld_s]
     int64_t ld_s;
+    int accumulate;            // complete rows start from y; split rows get y added by k_spmm_combine (base = y)
     __device__ __forceinline__ bool get(int64_t item, int32_t& b, int32_t& e, float*& dst) const {
         b = __ldg(item_begin + item);
         e = __ldg(item_end + item);
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
         const bool full_row = work.get(item, e_begin, e_end, yr);
         typename V::T acc[KCH];
 #pragma unroll
-        for (int k = 0; k < KCH; ++k) acc[k] = V::zero();
+        for (int k = 0; k < KCH; ++k) acc[k] = (work.accumulate && full_row && slot == 0 && colok[k]) ? V::load(yr + coff[k]) : V::zero();
         int buf = 0;
         // software pipeline: the (col, val) pair of the NEXT chunk is in flight while this chunk is gathered
         int nc = 0;
@@ -213,8 +215,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmm(const Work work, const 
 // with `partial` the CTAs also emit their column sums of the rows they finish (blocks first_blk .. first_blk+grid-1).
 __global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot,
                                const int32_t* __restrict__ long_cnt, int64_t n_long, const float* __restrict__ scratch,
-                               int64_t ld_s, float* __restrict__ y, int64_t ldy, int h, double* __restrict__ partial,
-                               int ldp, int first_blk, const float* __restrict__ base = nullptr, int64_t ldb = 0) {
+                               int64_t ld_s, float* y, int64_t ldy, int h, double* __restrict__ partial,
+                               int ldp, int first_blk, const float* base = nullptr, int64_t ldb = 0) {   // base may be y
     for (int c = threadIdx.x; c < h; c += blockDim.x) {
         double s = 0.0, q = 0.0;
         for (int64_t i = blockIdx.x; i < n_long; i += gridDim.x) {
@@ -365,7 +367,8 @@ static int64_t grid_cap(bool stats) {
 
 template <int G, int S, int VEC, int KCH, int MINB = 4, int UNR = 4>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
-           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st) {
+           int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st,
+           int accumulate = 0) {
     const int64_t n_items = plan ? plan->n_items : n_rows;
     const int64_t groups_per_block = kThreads / (G * S);
     int64_t blocks = ceil_div(n_items, groups_per_block);
@@ -388,11 +391,11 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* val, const fl
 #define GLASS_SPMM_GO2(E, I, ST)                                                                                      \
     do {                                                                                                              \
         if (plan) {                                                                                                   \
-            PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h};          \
+            PlanWork w{plan->item_begin, plan->item_end, plan->item_dst, y, ldy, plan->scratch, (int64_t)h, accumulate}; \
             k_spmm<G, S, VEC, KCH, E, I, MINB, UNR, ST, PlanWork>                                                     \
                 <<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h, partial, ldp);                           \
         } else {                                                                                                      \
-            RowWork w{rowptr, y, ldy};                                                                                \
+            RowWork w{rowptr, y, ldy, accumulate};                                                                    \
             k_spmm<G, S, VEC, KCH, E, I, MINB, UNR, ST, RowWork>                                                      \
                 <<<grid, kThreads, 0, st>>>(w, col, val, x, ldx, n_items, h, partial, ldp);                           \
         }                                                                                                             \
@@ -412,19 +415,21 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* val, const fl
     if (comb) {
         const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
         k_spmm_combine<<<(unsigned)n_comb, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long,
-                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, (int)grid);
+                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, (int)grid,
+                                                           accumulate ? y : nullptr, ldy);
         GLASS_LAUNCH_CHECK();
     }
     return GLASS_OK;
 }
 
 int dispatch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
-             int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st) {
+             int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st,
+             int accumulate = 0) {
     const bool vec = (h % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
                      ((uintptr_t)y % 16 == 0) && (!plan || (uintptr_t)plan->scratch % 16 == 0);
     const int64_t n_items = plan ? plan->n_items : n_rows;
     const bool par = latency_regime(n_items);
-#define ARGS rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, stats, st
+#define ARGS rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, plan, stats, st, accumulate
 #define GO(G, V, K)                                                                                                   \
     do {                                                                                                              \
         if (par && G < 32) return launch<G, 32 / G, V, K>(ARGS);                                                      \
@@ -636,10 +641,15 @@ extern "C" int glass_spmm_plan_build(const int32_t* rowptr, int64_t n_rows, int 
         }
         slot += c;
     }
-    for (int64_t r = 0; r < n_rows; ++r) {
-        if (rp[r + 1] - rp[r] > max_len) continue;
-        ib.push_back(rp[r]), ie.push_back(rp[r + 1]), id.push_back((int32_t)r);
-    }
+    // ... longest first (stable): the lane groups of a warp / CTA work on rows of nearly equal length -- in row order a
+    // CTA lives as long as the longest of its 16 random rows while the other groups idle (power-law em_user-shaped
+    // graph: achieved occupancy 42 %), and the grid's tail is made of the shortest rows
+    std::vector<int32_t> ord;
+    ord.reserve((size_t)n_rows);
+    for (int64_t r = 0; r < n_rows; ++r)
+        if (rp[r + 1] - rp[r] <= max_len) ord.push_back((int32_t)r);
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
+    for (int32_t r : ord) ib.push_back(rp[r]), ie.push_back(rp[r + 1]), id.push_back(r);
     auto up = [&](int32_t* dst, const std::vector<int32_t>& v) -> cudaError_t {
         if (v.empty()) return cudaSuccess;
         return cudaMemcpyAsync(dst, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, st);
@@ -674,4 +684,69 @@ extern "C" int glass_spmm_csr_planned(const int32_t* col, const float* val, cons
     Stats s{stats_partial, stats_ld, stats_nblk_host};
     return dispatch(nullptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, &p, stats_partial ? &s : nullptr,
                     as_stream(stream));
+}
+
+// ---- L2 gather probe (measurement aid) -----------------------------------------------------------------------------
+namespace glass {
+namespace {
+template <int G>
+__global__ void __launch_bounds__(kThreads, 5) k_l2_gather_probe(const float* __restrict__ x, uint32_t ldx, uint32_t n_rows,
+                                                               int64_t per_group, float* __restrict__ sink) {
+    const int lane = threadIdx.x & 31, l = lane & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+    // one multiplicative-congruential stream per lane group (the same value in all of its lanes)
+    uint32_t s = (uint32_t)group * 2654435761u + 12345u;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = 0; i < per_group; i += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = s * 1664525u + 1013904223u;
+            const uint32_t r = (uint32_t)(((uint64_t)s * n_rows) >> 32);
+            v[u] = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + l);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+    }
+    sink[(int64_t)blockIdx.x * kThreads + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
+}
+}  // namespace
+}  // namespace glass
+
+extern "C" int glass_l2_gather_probe(const float* x, int64_t ldx, int64_t n_rows, int h, int64_t gathers, float* sink,
+                                     int64_t sink_elems, void* stream) {
+    GLASS_CHECK_ARG(x && sink && n_rows > 0 && gathers > 0 && (h == 32 || h == 64 || h == 128) && ldx >= h && ldx % 4 == 0 &&
+                        (uintptr_t)x % 16 == 0 && n_rows * ldx < (1ll << 31),
+                    "l2_gather_probe: bad arguments");
+    const int g = h / 4;
+    const int64_t grid = (int64_t)sm_count() * 5;
+    GLASS_CHECK_ARG(sink_elems >= grid * kThreads, "l2_gather_probe: sink needs %lld floats", (long long)(grid * kThreads));
+    const int64_t groups = grid * kThreads / g;
+    const int64_t per_group = (ceil_div(gathers, groups) + 7) / 8 * 8;
+    cudaStream_t st = as_stream(stream);
+    if (g == 8) k_l2_gather_probe<8><<<(unsigned)grid, kThreads, 0, st>>>(x, (uint32_t)ldx, (uint32_t)n_rows, per_group, sink);
+    else if (g == 16) k_l2_gather_probe<16><<<(unsigned)grid, kThreads, 0, st>>>(x, (uint32_t)ldx, (uint32_t)n_rows, per_group, sink);
+    else k_l2_gather_probe<32><<<(unsigned)grid, kThreads, 0, st>>>(x, (uint32_t)ldx, (uint32_t)n_rows, per_group, sink);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
+// y (+)= A x: glass_spmm_csr / glass_spmm_csr_planned with an accumulate flag (column-partitioned phases of one product,
+// glass_b200/partition.py: the entries whose columns a peer owns are multiplied as that peer's shard arrives).
+// item_begin == NULL: plain CSR by rowptr; otherwise a row-split plan.  No statistics epilogue.
+extern "C" int glass_spmm_csr_acc(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx,
+                                  float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const int32_t* item_begin,
+                                  const int32_t* item_end, const int32_t* item_dst, int64_t n_items,
+                                  const int32_t* long_row, const int32_t* long_slot, const int32_t* long_cnt,
+                                  int64_t n_long, float* scratch, int accumulate, void* stream) {
+    GLASS_CHECK_ARG(x && y && n_rows >= 0 && n_cols > 0 && h > 0 && h <= 256 && ldx >= h && ldy >= h, "spmm_csr_acc: bad arguments");
+    const bool planned = item_begin != nullptr;
+    GLASS_CHECK_ARG(planned ? (col && val && item_end && item_dst && n_items >= n_rows &&
+                               (n_long == 0 || (long_row && long_slot && long_cnt && scratch)))
+                            : rowptr != nullptr,
+                    "spmm_csr_acc: give either rowptr or a complete row-split plan");
+    if (n_rows == 0) return GLASS_OK;
+    Plan p{item_begin, item_end, item_dst, n_items, long_row, long_slot, long_cnt, n_long, scratch};
+    return dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, n_cols, h, planned ? &p : nullptr, nullptr, as_stream(stream),
+                    accumulate ? 1 : 0);
 }

@@ -92,6 +92,12 @@ class SymmetricGradExchange:
         torch.cuda.synchronize(dev)
         dist.barrier(self.group)                                      # every rank's block is initialised
 
+    def release(self):
+        """Undo the constructor's side effects (table back in ordinary memory, gradient sink dropped)."""
+        if self.table is not None:
+            self.table.data = self.table.data.clone()
+            ops.unregister_grad_buffer(self.table_grad)
+
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None

@@ -79,13 +79,22 @@ class GraphedTrainStep:
         import os
         self.dp_mode = "none"
         if self.world > 1 and os.environ.get("GLASS_B200_DP", "symm") == "symm":
+            opt, why = None, ""
             try:
                 from .dp import SymmetricGradExchange
-                self.opt = SymmetricGradExchange(self.params, lr, betas, eps, weight_decay, group)
-                self.dp_mode = "symm"
-            except (NotImplementedError, ImportError, AttributeError) as e:
+                opt = SymmetricGradExchange(self.params, lr, betas, eps, weight_decay, group)
+            except (NotImplementedError, ImportError, AttributeError, RuntimeError) as e:
+                why = str(e)
+            # the choice is collective: one rank without peer-mapped memory sends every rank to the NCCL path
+            ok = torch.tensor([1 if opt is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self.opt, self.dp_mode = opt, "symm"
+            else:
                 import warnings
-                warnings.warn(f"symmetric-memory gradient exchange unavailable ({e}); using NCCL all-reduce")
+                warnings.warn(f"symmetric-memory gradient exchange unavailable ({why or 'on a peer rank'}); using NCCL all-reduce")
+                if opt is not None:
+                    opt.release()
         if self.dp_mode == "none":
             if self.world > 1:
                 self.averager = GradAverager(self.params, group)

@@ -137,6 +137,24 @@ _define("spmm_csr_planned_(Tensor col, Tensor val, Tensor x, Tensor(a!) y, Tenso
         "Tensor(c!)? partial) -> int", _spmm_csr_planned_)
 
 
+def _spmm_csr_acc_(rowptr, col, val, x, y, item_begin, item_end, item_dst, long_row, long_slot, long_cnt, scratch,
+                   accumulate):
+    """y (+)= A x, plain CSR (item_begin None) or row-split plan; see glass_spmm_csr_acc."""
+    lib = _lib.load()
+    n_rows, h = y.shape
+    planned = item_begin is not None
+    check(lib.glass_spmm_csr_acc(_p(rowptr), _p(col), _p(val), _p(x), x.stride(0), _p(y), y.stride(0), n_rows, x.shape[0],
+                                 h, _p(item_begin), _p(item_end), _p(item_dst), item_begin.numel() if planned else 0,
+                                 _p(long_row), _p(long_slot), _p(long_cnt), long_row.numel() if planned else 0,
+                                 _p(scratch), 1 if accumulate else 0, _stream()), "spmm_csr_acc")
+    _count(2 if planned else 1)
+
+
+_define("spmm_csr_acc_(Tensor? rowptr, Tensor col, Tensor val, Tensor x, Tensor(a!) y, Tensor? item_begin, "
+        "Tensor? item_end, Tensor? item_dst, Tensor? long_row, Tensor? long_slot, Tensor? long_cnt, "
+        "Tensor(b!)? scratch, bool accumulate) -> ()", _spmm_csr_acc_)
+
+
 def _spmm_delta_(rowptr, col, val, mask, delta, base, y, item_begin, item_end, item_dst, long_row, long_slot, long_cnt,
                  scratch, partial):
     """y = base + adj[:, mask] @ delta[mask]  (sparse label correction)."""
@@ -544,7 +562,16 @@ def to_undirected(edge_index: torch.Tensor, edge_weight: torch.Tensor, n_node: i
 # ---------------------------------------------------------------------------------------------
 # autograd building blocks
 # ---------------------------------------------------------------------------------------------
-def _run_spmm(rowptr, col, val, plan, x, y, partial=None) -> int:
+def _run_spmm(rowptr, col, val, plan, x, y, partial=None, accumulate: bool = False) -> int:
+    """y = A x (accumulate: y += A x, no statistics).  `plan`: RowSplitPlan of this CSR or None."""
+    if accumulate:
+        if plan is None:
+            _ops.spmm_csr_acc_(rowptr, col, val, x, y, None, None, None, None, None, None, None, True)
+        else:
+            scratch = torch.empty((plan.n_slots, y.shape[1]), dtype=torch.float32, device=y.device)
+            _ops.spmm_csr_acc_(None, col, val, x, y, plan.item_begin, plan.item_end, plan.item_dst, plan.long_row,
+                               plan.long_slot, plan.long_cnt, scratch, True)
+        return 0
     if plan is None:
         return _ops.spmm_csr_(rowptr, col, val, x, y, partial)
     scratch = torch.empty((plan.n_slots, y.shape[1]), dtype=torch.float32, device=y.device)
@@ -765,6 +792,11 @@ def register_grad_buffer(param: torch.Tensor, buffer: torch.Tensor) -> None:
     for k in [k for k, (ref, _) in _grad_sinks.items() if ref() is None]:      # parameters that no longer exist
         del _grad_sinks[k]
     _grad_sinks[param.data_ptr()] = (weakref.ref(param), buffer)
+
+
+def unregister_grad_buffer(buffer: torch.Tensor) -> None:
+    for k in [k for k, (_, b) in _grad_sinks.items() if b is buffer]:
+        del _grad_sinks[k]
 
 
 def _grad_sink_for(x: torch.Tensor):

@@ -42,9 +42,28 @@ def _block(rowptr, col, val, lo, hi, remap):
     return rp, c, val[s:e].contiguous()
 
 
+def split_columns_by_owner(rp, c, v, bounds, rebase: bool = True):
+    """Split a CSR block by column range: part s holds the entries with bounds[s] <= column < bounds[s + 1] (columns
+    re-based to bounds[s] when `rebase`: they then index owner s's own feature shard).  Entry order inside a row is
+    kept.  Returns [(rowptr int32, col int32, val)] * (len(bounds) - 1)."""
+    n_rows = rp.numel() - 1
+    counts = (rp[1:] - rp[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=c.device), counts)
+    edges = torch.tensor(list(bounds[1:-1]), dtype=c.dtype, device=c.device)
+    owner = torch.bucketize(c, edges, right=True)
+    out = []
+    for s_ in range(len(bounds) - 1):
+        sel = owner == s_
+        cnt = torch.bincount(rows[sel], minlength=n_rows)
+        rp_new = torch.zeros(n_rows + 1, dtype=torch.int64, device=c.device)
+        torch.cumsum(cnt, 0, out=rp_new[1:])
+        shift = int(bounds[s_]) if rebase else 0
+        out.append((rp_new.to(torch.int32), (c[sel] - shift).to(torch.int32).contiguous(), v[sel].contiguous()))
+    return out
+
+
 def _split_columns(rp, c, v, lo_col: int, hi_col: int):
-    """Split a CSR block into the entries whose column lies in [lo_col, hi_col) -- re-based to 0, they index
-    this rank's own feature shard -- and the rest (columns unchanged).  Entry order inside a row is kept."""
+    """(own, rest): the entries whose column lies in [lo_col, hi_col), re-based to 0, and all others (columns unchanged)."""
     n_rows = rp.numel() - 1
     counts = (rp[1:] - rp[:-1]).long()
     rows = torch.repeat_interleave(torch.arange(n_rows, device=c.device), counts)
@@ -59,6 +78,48 @@ def _split_columns(rp, c, v, lo_col: int, hi_col: int):
     return pick(own, lo_col), pick(~own, 0)
 
 
+class PeerExchange:
+    """Feature-shard exchange of the pipelined row-partitioned SpMM over NVLink peer memory.
+
+    Every rank publishes its [pad, h] shard in a symmetric (peer-mapped) buffer; after one device-side barrier each
+    rank PULLS the peers' shards with copy-engine transfers on side streams, one event per source, in the order
+    rank+1, rank+2, ...  so that the SpMM phase of source s starts as soon as shard s has landed while the other
+    transfers are still in flight.  Two buffer generations alternate: a rank may publish the next product's shard
+    while slower peers still read the previous one (the barrier of product k+1 proves every pull of product k is
+    complete before generation k % 2 is written again).  torch.distributed._symmetric_memory only provides the
+    allocation, the address exchange and the barrier; no library collective moves data."""
+
+    def __init__(self, pad: int, h: int, rank: int, world: int, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.pad, self.h, self.rank, self.world = pad, h, rank, world
+        self.group = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty((2, pad, h), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.order = [(rank + i) % world for i in range(1, world)]
+        self.peer = {s: [self.handle.get_buffer(s, (pad, h), torch.float32, g * pad * h) for g in range(2)] for s in self.order}
+        self.stage = {s: torch.empty((pad, h), dtype=torch.float32, device=device) for s in self.order}
+        self.streams = {s: torch.cuda.Stream(device=device) for s in self.order}
+        self.gen = 0
+
+    def start(self, send: torch.Tensor):
+        """send [pad, h] (this rank's padded shard).  Returns [(source rank, shard tensor, wait())] own shard first."""
+        main = torch.cuda.current_stream(send.device)
+        g = self.gen
+        self.gen ^= 1
+        self.buf[g].copy_(send)
+        self.handle.barrier(channel=0, timeout_ms=20000)     # every rank's generation-g shard is complete (traps, not hangs)
+        out = [(self.rank, send, lambda: None)]
+        for s in self.order:
+            st = self.streams[s]
+            st.wait_stream(main)                             # after the barrier, and after the last reader of stage[s]
+            with torch.cuda.stream(st):
+                self.stage[s].copy_(self.peer[s][g], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            out.append((s, self.stage[s], (lambda e=ev: main.wait_event(e))))
+        return out
+
+
 class RowPartitionedAdj:
     """This rank's row blocks of A and A^T with columns remapped to the padded all-gather layout.
 
@@ -70,7 +131,8 @@ class RowPartitionedAdj:
     local L2, so every remote entry would pull its 256-byte row over NVLink (12.8 GB per SpMM at N = 2 on the
     stress graph) against 256 MB for the all-gather."""
 
-    def __init__(self, adj: ops.CSRAdj, rank: int, world: int, group=None, overlap: bool = False):
+    def __init__(self, adj: ops.CSRAdj, rank: int, world: int, group=None, overlap: bool = False,
+                 pipelined: bool = False):
         self.rank, self.world, self.group, self.n = rank, world, group, adj.n
         dev = adj.col.device
         self.bounds = balanced_row_splits(adj.rowptr, world)
@@ -90,6 +152,16 @@ class RowPartitionedAdj:
         self.nnz_local = int(blk[1].numel())
         self.gather_override = None     # tests: callable(padded_local) -> [world * pad, H] without a process group
         self.own = self.rem = None
+        # pipelined: one sub-block per SOURCE rank (columns re-based to that rank's shard); the product is taken in
+        # `world` phases that accumulate into y, phase s as soon as shard s has arrived (PeerExchange)
+        self.phases = None
+        self.exchange = {}                 # h -> PeerExchange
+        self.exchange_override = None      # tests: callable(padded_local) -> [world shards] without peer memory
+        if pipelined:
+            bounds = [s_ * self.pad for s_ in range(world + 1)]
+            fwd = split_columns_by_owner(*blk, bounds)
+            bwd = split_columns_by_owner(*blk_t, bounds)
+            self.phases = [ops.CSRAdj(self.rows, *f, *b, none, adj.aggr).make_plans() for f, b in zip(fwd, bwd)]
         if overlap:
             lo_col = rank * self.pad
             (o, r), (ot, rt) = _split_columns(*blk, lo_col, lo_col + self.rows), _split_columns(*blk_t, lo_col, lo_col + self.rows)
@@ -128,6 +200,34 @@ class RowPartitionedAdj:
         ops._run_spmm(rem.rowptr, rem.col, rem.val, rem.plan, full, y2)
         return y.add_(y2)
 
+    def _pad(self, local: torch.Tensor) -> torch.Tensor:
+        if self.rows == self.pad:
+            return local.contiguous()
+        send = torch.zeros((self.pad, local.shape[1]), dtype=local.dtype, device=local.device)
+        send[:self.rows] = local
+        return send
+
+    def _spmm_pipelined(self, v_local: torch.Tensor, transposed: bool) -> torch.Tensor:
+        h = v_local.shape[1]
+        send = self._pad(v_local)
+        if self.exchange_override is not None:
+            shards = self.exchange_override(send)
+            order = [self.rank] + [(self.rank + i) % self.world for i in range(1, self.world)]
+            arrivals = [(s_, shards[s_], (lambda: None)) for s_ in order]
+        elif self.world == 1:
+            arrivals = [(0, send, (lambda: None))]
+        else:
+            ex = self.exchange.get(h)
+            if ex is None:
+                ex = self.exchange[h] = PeerExchange(self.pad, h, self.rank, self.world, self.group, v_local.device)
+            arrivals = ex.start(send)
+        y = torch.empty((self.rows, h), dtype=torch.float32, device=v_local.device)
+        for i, (src, shard, wait) in enumerate(arrivals):
+            wait()
+            a = self.phases[src].t() if transposed else self.phases[src]
+            ops._run_spmm(a.rowptr, a.col, a.val, a.plan, shard, y, accumulate=i > 0)
+        return y
+
     def _gather(self, local: torch.Tensor) -> torch.Tensor:
         out, wait = self._gather_async(local)
         wait()
@@ -142,6 +242,8 @@ class _PartSpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, part: RowPartitionedAdj):
         ctx.part = part
+        if part.phases is not None:
+            return part._spmm_pipelined(x_local, False)
         if part.own is not None:
             return part._spmm_overlapped(x_local, False)
         x_full = part._gather(x_local)
@@ -153,6 +255,8 @@ class _PartSpMM(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         part = ctx.part
+        if part.phases is not None:
+            return part._spmm_pipelined(gy.contiguous(), True), None
         if part.own is not None:
             return part._spmm_overlapped(gy.contiguous(), True), None
         gy_full = part._gather(gy.contiguous())

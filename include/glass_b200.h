@@ -102,7 +102,7 @@ int glass_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, 
  * partial sums go to a scratch matrix [n_slots, h] and are added up in chunk order (deterministic).
  * Init path (reads rowptr back to the host): glass_spmm_plan_size returns the array sizes,
  * glass_spmm_plan_build fills item_begin/item_end/item_dst [n_items] (heavy items first; item_dst >= 0 is
- * a row of y, < 0 is scratch row -1-item_dst) and long_row/long_slot/long_cnt [n_long].
+ * a row of y, < 0 is scratch row -1-item_dst; ordinary rows follow longest first) and long_row/long_slot/long_cnt [n_long].
  * glass_spmm_csr_planned is glass_spmm_csr driven by that plan (capturable; scratch from the caller). */
 int glass_spmm_plan_size(const int32_t* rowptr, int64_t n_rows, int max_len, int64_t* n_items_host,
                          int64_t* n_long_host, int64_t* n_slots_host, void* stream);
@@ -115,6 +115,21 @@ int glass_spmm_csr_planned(const int32_t* col, const float* val, const float* x,
                            const int32_t* long_row, const int32_t* long_slot, const int32_t* long_cnt,
                            int64_t n_long, float* scratch, double* stats_partial, int stats_ld,
                            int* stats_nblk_host, void* stream);
+
+/* y (+)= A x for plain (item_begin == NULL) or planned CSR: the column-partitioned phases of one product
+ * (glass_b200/partition.py multiplies a peer's columns as soon as that peer's feature shard has arrived). */
+int glass_spmm_csr_acc(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx,
+                       float* y, int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const int32_t* item_begin,
+                       const int32_t* item_end, const int32_t* item_dst, int64_t n_items, const int32_t* long_row,
+                       const int32_t* long_slot, const int32_t* long_cnt, int64_t n_long, float* scratch,
+                       int accumulate, void* stream);
+
+/* Measurement aid (bench.py `roofline.l2_gather`): `gathers` pseudo-random 4*h-byte rows of x[n_rows, ldx] are read
+ * by lane groups exactly as glass_spmm_csr gathers neighbour rows (float4 per lane, 8 loads in flight) and summed
+ * into sink[grid * 256]; no index or value stream, no dependent FMA chain per row -- the L2 -> SM gather rate the
+ * SpMM could reach at best on this device.  h in {32, 64, 128}. */
+int glass_l2_gather_probe(const float* x, int64_t ldx, int64_t n_rows, int h, int64_t gathers, float* sink,
+                          int64_t sink_elems, void* stream);
 
 /* Sparse label correction for multi-label-batch evaluation (reference
  * impl/train.py:20-34 evaluates every label batch with a full adj @ x).  For fixed weights the mixed features of two

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--check", action="store_true", help="compare with the replicated single-GPU SpMM")
     ap.add_argument("--overlap", action="store_true", help="multiply locally-owned columns while the all-gather runs")
+    ap.add_argument("--pipelined", action="store_true",
+                    help="peer-memory pulls per source rank, one accumulating SpMM phase per arrived shard")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -37,7 +39,7 @@ def main():
     adj = ops.build_csr(g.edge_index.to(dev), g.edge_attr.to(dev), n, "gcn")
     torch.cuda.synchronize()
     t_build = time.time() - t0
-    part = RowPartitionedAdj(adj, rank, world, overlap=args.overlap)
+    part = RowPartitionedAdj(adj, rank, world, overlap=args.overlap, pipelined=args.pipelined)
     x = torch.randn(n, h, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
     xs = part.shard(x)
     err = None
@@ -77,7 +79,7 @@ def main():
         nnz = int(g.edge_index.shape[1])
         algo = 4 * (n + 1) + 8 * nnz + 8 * n * h
         print(json.dumps({"metric": "row-partitioned SpMM (all-gather + local block SpMM)", "graph": args.graph,
-                          "overlap": args.overlap, "nodes": n, "nnz": nnz, "h": h, "n_gpus": world, "ms_per_spmm": float(ms),
+                          "overlap": args.overlap, "pipelined": args.pipelined, "nodes": n, "nnz": nnz, "h": h, "n_gpus": world, "ms_per_spmm": float(ms),
                           "ms_allgather": float(gms), "algorithmic_GBps_aggregate": algo / float(ms) / 1e6,
                           "rows_per_rank_pad": part.pad, "nnz_rank0": part.nnz_local, "check_rel_err": err,
                           "gen_s": t_gen, "csr_build_s": t_build}), flush=True)

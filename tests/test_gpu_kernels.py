@@ -195,6 +195,33 @@ def test_spmm_row_split_plan_matches_plain_kernel(h):
     assert ops.build_csr(ei2.to(DEV), ew2.to(DEV), 2000, "sum").plan is None
 
 
+@pytest.mark.parametrize("h,planned", [(64, False), (64, True), (17, False), (8, True)])
+def test_spmm_accumulate_column_phases(h, planned):
+    """y (+)= A x (glass_spmm_csr_acc): the product taken as column-partitioned phases -- first the entries whose
+    column is < n/3, then the middle third, then the rest, each accumulating into y -- equals adj @ x (oracle,
+    impl/models.py:164).  This is how the row-partitioned SpMM consumes the peers' feature shards as they arrive."""
+    from glass_b200 import datasets, ops
+    from glass_b200.partition import split_columns_by_owner
+    n = 3000
+    e = datasets.powerlaw_edges(n, 40000, 7)
+    ei, ew = datasets.coalesce_undirected(e, torch.ones(e.shape[1]), n)
+    adj = ops.build_csr(ei.to(DEV), ew.to(DEV), n, "gcn")
+    x = torch.randn(n, h, generator=torch.Generator().manual_seed(8)).to(DEV)
+    bounds = [0, 1000, 2000, 3000]
+    subs = split_columns_by_owner(adj.rowptr, adj.col, adj.val, bounds, rebase=False)
+    y = torch.full((n, h), 7.0, device=DEV)                      # the first phase overwrites
+    for i, (rp, c, v) in enumerate(subs):
+        plan = None
+        if planned:
+            p = ops.RowSplitPlan(rp, 32)
+            plan = p if p.n_long else None
+        if i == 0:
+            ops._run_spmm(rp, c, v, plan, x, y)
+        else:
+            ops._run_spmm(rp, c, v, plan, x, y, accumulate=True)
+    assert rel_err(y.cpu(), O.build_adj(ei, ew, n, "gcn") @ x.cpu()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------ pair GEMM
 def _pair_ref(a, w0, b0, w1, b1, mask, z, act):
     f = {0: (lambda t: t), 1: torch.relu, 2: torch.nn.functional.elu}[act]
@@ -410,11 +437,12 @@ def test_labels_and_pad2batch_known_answers():
 
 
 # ------------------------------------------------------------------------------------------ row partitioning
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap", [False, True, "pipelined"])
 @pytest.mark.parametrize("world", [1, 3, 4])
 def test_row_partitioned_spmm_single_device_emulation(world, overlap):
     """All ranks' blocks built on one GPU; the all-gather is emulated by concatenating the padded shards.
-    overlap=True multiplies the locally-owned columns first (while the gather would be in flight)."""
+    overlap=True multiplies the locally-owned columns first (while the gather would be in flight); "pipelined" takes
+    the product in one accumulating phase per source rank (own shard first, then rank+1, ...)."""
     from glass_b200 import datasets, ops
     from glass_b200.partition import RowPartitionedAdj
     n, h = 6000, 64
@@ -427,10 +455,13 @@ def test_row_partitioned_spmm_single_device_emulation(world, overlap):
     xf = x.cpu().requires_grad_(True)
     y_ref = O.build_adj(ei, ew, n, "mean") @ xf
     y_ref.backward(gy.cpu())
-    parts = [RowPartitionedAdj(adj, r, world, overlap=overlap) for r in range(world)]
+    pipelined = overlap == "pipelined"
+    parts = [RowPartitionedAdj(adj, r, world, overlap=overlap is True, pipelined=pipelined) for r in range(world)]
     nnz = [p.nnz_local for p in parts]
-    if overlap:
+    if overlap is True:
         assert all(p.own.nnz + p.rem.nnz == p.nnz_local for p in parts)
+    if pipelined:
+        assert all(sum(ph.nnz for ph in p.phases) == p.nnz_local for p in parts)
     assert sum(nnz) == adj.nnz and max(nnz) <= 1.3 * adj.nnz / world + 4096      # balanced by entries
     pad = parts[0].pad
 
@@ -451,6 +482,7 @@ def test_row_partitioned_spmm_single_device_emulation(world, overlap):
             return full
 
         p.gather_override = fake_gather
+        p.exchange_override = lambda send, fg=fake_gather: list(fg(send).split(pad))
         y = p.spmm(xs)
         assert rel_err(y.detach().cpu(), y_ref[p.lo:p.hi].detach()) < 1e-5
         y.backward(gy[p.lo:p.hi].contiguous())

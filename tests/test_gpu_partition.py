@@ -48,7 +48,7 @@ class ReplayComm:
         return torch.cat(parts, dim=0)
 
 
-def _run_partitioned(case, world, p_drop=0.0, keeps=None):
+def _run_partitioned(case, world, p_drop=0.0, keeps=None, pipelined=False):
     """Sweeps until the recorded collectives stop changing; returns (logits of rank 0, summed parameter gradients)."""
     from glass_b200 import ops, utils
     from glass_b200.partition import PartitionedGLASS, RowPartitionedAdj
@@ -61,7 +61,7 @@ def _run_partitioned(case, world, p_drop=0.0, keeps=None):
     model.load_state_dict(c["sd"])
     model = model.to(DEV).train()
     adj = ops.build_csr(ei, ew, n, c["raw"]["aggr"])
-    parts = [RowPartitionedAdj(adj, r, world) for r in range(world)]
+    parts = [RowPartitionedAdj(adj, r, world, pipelined=pipelined) for r in range(world)]
     table = model.conv.input_emb.weight
     ids = c["x"].reshape(-1).to(DEV)
     loss_fn = O.loss_fn_for(c["cfg"].out_dim == 1)
@@ -71,6 +71,7 @@ def _run_partitioned(case, world, p_drop=0.0, keeps=None):
         for r in range(world):
             comm = ReplayComm(world, r, prev)
             parts[r].gather_override = comm.all_gather
+            parts[r].exchange_override = lambda send, c_=comm, p_=parts[r]: list(c_.all_gather(send).split(p_.pad))
             pm = PartitionedGLASS(model, parts[r], comm)
             model.zero_grad(set_to_none=True)
             h_local = table[ids[parts[r].lo:parts[r].hi]]                    # this rank's rows of the input embedding
@@ -103,10 +104,12 @@ def _run_partitioned(case, world, p_drop=0.0, keeps=None):
     return result[0][0], total, model
 
 
-@pytest.mark.parametrize("name,world", [("ppibp_like", 3), ("emuser_like", 2), ("cutratio_like", 4)])
-def test_partitioned_model_matches_reference_golden(name, world):
+@pytest.mark.parametrize("name,world,pipelined", [("ppibp_like", 3, False), ("emuser_like", 2, False),
+                                                  ("cutratio_like", 4, False), ("ppibp_like", 3, True),
+                                                  ("emuser_like", 4, True)])
+def test_partitioned_model_matches_reference_golden(name, world, pipelined):
     c = load_model_case(name)
-    logits, grads, model = _run_partitioned(c, world)
+    logits, grads, model = _run_partitioned(c, world, pipelined=pipelined)
     assert rel_err(logits.cpu(), c["logits"]) < 1e-4
     table_key = "conv.input_emb.weight"
     for k, g in grads.items():
