@@ -401,7 +401,7 @@ def run_product(args):
                        "api": "glass_b200.graphed.train_epoch(GraphedTrainStep, pinned host batches), loss.item() every step"}
         line["cuda_graph"] = not args.no_graph
         if world > 1:   # "symm": fused reduce-scatter + Adam + all-gather over NVLink peer memory; "nccl": all-reduce, then Adam
-            line["config"]["grad_exchange"] = step.dp_mode
+            line["grad_exchange"] = step.dp_mode
         line["gpu_launches"] = launches
         line["clocks"] = clocks.summary()
         adj = model.conv.convs[0].adj

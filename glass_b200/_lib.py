@@ -77,6 +77,9 @@ PROTOTYPES = {
     "glass_segment_pool_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _i64, _vp]),
     "glass_segment_pool_bwd_scratch_bytes": (_sz, [_i64, _i64]),
     "glass_segment_pool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _vp, _sz, _vp]),
+    "glass_norm_pool_fwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _i64, _vp]),
+    "glass_norm_pool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp,
+                                   _vp, _i32, _i64, _vp, _sz, _vp]),
     "glass_segment_pool_batch_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
     "glass_segment_pool_batch_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "glass_adam_chunk": (_i32, []),

@@ -85,6 +85,9 @@ __device__ __forceinline__ float act_grad_from_pre(float v, int act) {
     return 1.f;
 }
 
+// rows of the GraphNorm statistics table stats[6, c] (graphnorm.cu writes it; pool.cu / gemm_tc.cu consume it)
+enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4, ST_RNG = 5 };
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

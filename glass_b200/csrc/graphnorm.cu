@@ -25,8 +25,7 @@ constexpr int kThreads = 256;
 constexpr int kSumThreads = 256;      // k_colsums; 512 threads per CTA measured slower (em_user bwd 14.6 -> 19.2 us per launch)
 constexpr int kMaxPartialCtas = 296;  // 2 CTAs per SM on 148 SMs (4 per SM measured slower); fixed so the workspace size is device independent
 
-// stats rows
-enum { ST_SCALE = 0, ST_AM = 1, ST_MU = 2, ST_RSTD = 3, ST_BIAS = 4, ST_RNG = 5 };
+// stats rows: ST_* in common.cuh
 
 // Dropout keep decision.  Either an explicit uint8 mask (tests inject one so that a train-mode pass can be
 // compared element-wise with the oracle) or a counter-based generator: Philox4x32-10 keyed by a per-device

@@ -234,6 +234,40 @@ __global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32
     }
 }
 
+// The same sum for widths h = 4 G (G a power of two <= 32) without statistics: one lane group per long row and a float4
+// per lane, four scratch rows in flight, added in chunk order (bit-identical to k_spmm_combine).  The column-per-thread
+// kernel above walks 16 long rows per CTA one after the other on h threads: 14 us for the 2,345 split rows of the
+// power-law em_user-shaped graph.
+template <int G>
+__global__ void __launch_bounds__(kThreads) k_spmm_combine_vec(const int32_t* __restrict__ long_row,
+                                                               const int32_t* __restrict__ long_slot,
+                                                               const int32_t* __restrict__ long_cnt, int64_t n_long,
+                                                               const float* __restrict__ scratch, int64_t ld_s, float* y,
+                                                               int64_t ldy, const float* base, int64_t ldb) {
+    const int l = threadIdx.x & (G - 1);
+    const int64_t groups = (int64_t)gridDim.x * (kThreads / G);
+    for (int64_t i = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; i < n_long; i += groups) {
+        const int32_t r = __ldg(long_row + i), s0 = __ldg(long_slot + i), cnt = __ldg(long_cnt + i);
+        float4 acc = base ? *reinterpret_cast<const float4*>(base + (int64_t)r * ldb + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* src = reinterpret_cast<const float4*>(scratch + (int64_t)s0 * ld_s) + l;
+        const int64_t step = ld_s >> 2;
+        int k = 0;
+        for (; k + 4 <= cnt; k += 4) {
+            const float4 a = __ldg(src + (int64_t)k * step), b = __ldg(src + (int64_t)(k + 1) * step);
+            const float4 c = __ldg(src + (int64_t)(k + 2) * step), d = __ldg(src + (int64_t)(k + 3) * step);
+            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+            acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+            acc.x += c.x, acc.y += c.y, acc.z += c.z, acc.w += c.w;
+            acc.x += d.x, acc.y += d.y, acc.z += d.z, acc.w += d.w;
+        }
+        for (; k < cnt; ++k) {
+            const float4 a = __ldg(src + (int64_t)k * step);
+            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+        }
+        *reinterpret_cast<float4*>(y + (int64_t)r * ldy + 4 * l) = acc;
+    }
+}
+
 // Sparse label correction (reference impl/train.py:20-34 + impl/models.py:161-164).
 // For fixed weights the label-mixed features of two label batches differ only on the labelled rows:
 //   x_b = U + [labelled] * delta,   so   adj @ x_b = adj @ U + adj[:, labelled] @ delta[labelled]
@@ -365,6 +399,36 @@ static int64_t grid_cap(bool stats) {
     return stats ? (int64_t)sm_count() * 5 * 2 : (int64_t)sm_count() * 8 * 4;
 }
 
+// combine launcher: the lane-group kernel when no statistics are wanted and the rows are float4-addressable
+static int launch_combine(const Plan* plan, float* y, int64_t ldy, int h, double* partial, int ldp, int first_blk,
+                          const float* base, int64_t ldb, cudaStream_t st) {
+    const int g = h / 4;
+    const bool vec = !partial && h % 4 == 0 && g >= 1 && g <= 32 && (g & (g - 1)) == 0 && ldy % 4 == 0 && (uintptr_t)y % 16 == 0 &&
+                     (uintptr_t)plan->scratch % 16 == 0 && (!base || (ldb % 4 == 0 && (uintptr_t)base % 16 == 0));
+    if (vec) {
+        const int64_t per = kThreads / g;
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(plan->n_long, per), (int64_t)sm_count() * 8);
+#define GO(G) k_spmm_combine_vec<G><<<grid, kThreads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long, \
+                                                              plan->scratch, (int64_t)h, y, ldy, base, ldb)
+        switch (g) {
+            case 1: GO(1); break;
+            case 2: GO(2); break;
+            case 4: GO(4); break;
+            case 8: GO(8); break;
+            case 16: GO(16); break;
+            default: GO(32); break;
+        }
+#undef GO
+    } else {
+        const int n_comb = (int)std::min<int64_t>(plan->n_long, kCombineCtas);
+        const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
+        k_spmm_combine<<<(unsigned)n_comb, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long,
+                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, first_blk, base, ldb);
+    }
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
 template <int G, int S, int VEC, int KCH, int MINB = 4, int UNR = 4>
 int launch(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
            int64_t ldy, int64_t n_rows, int64_t n_cols, int h, const Plan* plan, const Stats* stats, cudaStream_t st,
@@ -412,13 +476,7 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* val, const fl
 #undef GLASS_SPMM_GO
 #undef GLASS_SPMM_GO2
     GLASS_LAUNCH_CHECK();
-    if (comb) {
-        const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
-        k_spmm_combine<<<(unsigned)n_comb, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long,
-                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, (int)grid,
-                                                           accumulate ? y : nullptr, ldy);
-        GLASS_LAUNCH_CHECK();
-    }
+    if (comb) return launch_combine(plan, y, ldy, h, partial, ldp, (int)grid, accumulate ? y : nullptr, ldy, st);
     return GLASS_OK;
 }
 
@@ -541,13 +599,7 @@ int launch_delta(const int32_t* rowptr, const int32_t* col, const float* val, co
         else k_spmm_delta<G, false, RowWork><<<grid, kThreads, 0, st>>>(w, col, val, mask, delta, ldd, base, ldb, n_items, h, partial, ldp);
     }
     GLASS_LAUNCH_CHECK();
-    if (comb) {
-        const int threads = h <= 32 ? 32 : (h >= 256 ? 256 : (h + 31) / 32 * 32);
-        k_spmm_combine<<<(unsigned)n_comb, threads, 0, st>>>(plan->long_row, plan->long_slot, plan->long_cnt, plan->n_long,
-                                                           plan->scratch, (int64_t)h, y, ldy, h, partial, ldp, (int)grid,
-                                                           base, ldb);
-        GLASS_LAUNCH_CHECK();
-    }
+    if (comb) return launch_combine(plan, y, ldy, h, partial, ldp, (int)grid, base, ldb, st);
     return GLASS_OK;
 }
 }  // namespace

@@ -8,6 +8,8 @@ There is no torch.sparse / PyG / CPU fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -54,6 +56,7 @@ class GraphNorm(nn.Module):
 
 
 _adj_cache = {}
+_fuse_norm_pool = os.environ.get("GLASS_B200_NORM_POOL", "1") != "0"     # last GraphNorm + pooling as one operator
 
 
 def buildAdj(edge_index, edge_weight, n_node: int, aggr: str):
@@ -215,8 +218,11 @@ class EmbZGConv(nn.Module):
             h = ops.embedding(ids, self.input_emb.weight).reshape(n, -1)                    # :248
         return self.emb_gn(h, p=self.dropout, training=self.training)                       # :249-251
 
-    def _layers(self, h, edge_index, edge_weight, mask, first=None):
-        """:253-272 from the output of _input on; `first` replaces the call of convs[0] (shared-base evaluation)."""
+    def _layers(self, h, edge_index, edge_weight, mask, first=None, pool_to=None):
+        """:253-272 from the output of _input on; `first` replaces the call of convs[0] (shared-base evaluation).
+        pool_to = (subG_node, mode): return the POOLED output of the last GraphNorm instead of the [N, D] embedding --
+        that norm feeds nothing but GLASS.Pool (:266 / :272 -> :346-350), so it is applied to the gathered rows only
+        (ops.graph_norm_pool)."""
         act = _act_id(self.activation)
         xs = []
         for layer, conv in enumerate(self.convs):
@@ -226,12 +232,21 @@ class EmbZGConv(nn.Module):
                 h = self.gns[layer](h, act=act, p=self.dropout, training=self.training)
         last = self.gns[-1]
         if self.jk and len(xs) > 1:                                                         # :263-267
-            return ops.graph_norm_cat(xs, last.weight, last.bias, last.mean_scale, last.eps)
+            emb = ops.graph_norm_cat(xs, last.weight, last.bias, last.mean_scale, last.eps)
+            return emb if pool_to is None else ops.segment_pool(emb, *pool_to)
+        if pool_to is not None:
+            return ops.graph_norm_pool(xs[-1], last.weight, last.bias, last.mean_scale, last.eps, *pool_to)
         return last(xs[-1])                                                                 # :268-272
 
     def forward(self, x, edge_index, edge_weight, z=None):
         h = self._input(x)
         return self._layers(h, edge_index, edge_weight, self._mask(x.shape[0], z, x.device))
+
+    def forward_pooled(self, x, edge_index, edge_weight, z, subG_node, mode: str):
+        """Pool(forward(x, ...), subG_node) for the padded sum / mean / size pools without materialising the output of
+        the last GraphNorm (see _layers)."""
+        h = self._input(x)
+        return self._layers(h, edge_index, edge_weight, self._mask(x.shape[0], z, x.device), pool_to=(subG_node, mode))
 
     @torch.no_grad()
     def shared_base(self, x, edge_index, edge_weight):
@@ -328,7 +343,16 @@ class _SubgraphModel(nn.Module):
         return embs[0] if copies == 1 else torch.mean(torch.stack(embs, dim=1), dim=1)
 
     def forward(self, x, edge_index, edge_weight, subG_node, z=None, id=0):
-        pooled = self.Pool(self.NodeEmb(x, edge_index, edge_weight, z), subG_node, self.pools[id])
+        pool = self.pools[id]
+        mode = pool.padded_mode() if isinstance(pool, PoolModule) else None
+        if (mode in ops.NORM_POOL_MODES and x.shape[1] == 1 and hasattr(self.conv, "forward_pooled")
+                and type(self).Pool is GLASS.Pool and _fuse_norm_pool):
+            # one feature copy (always, on this path) and a padded sum / mean / size pool: the last GraphNorm and the
+            # pooling run as one operator (same values as Pool(NodeEmb(...)))
+            n, _, width = x.shape
+            pooled = self.conv.forward_pooled(x[:, 0, :].reshape(n, width), edge_index, edge_weight, z, subG_node, mode)
+        else:
+            pooled = self.Pool(self.NodeEmb(x, edge_index, edge_weight, z), subG_node, pool)
         return self.preds[id](pooled)
 
 

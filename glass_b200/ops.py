@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
 
-__all__ = ["CSRAdj", "build_csr", "to_undirected", "spmm", "spmm_graph_norm", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
+__all__ = ["CSRAdj", "build_csr", "to_undirected", "spmm", "spmm_graph_norm", "graph_norm_pool", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
            "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",
            "set_gemm_path", "launch_count", "reset_launch_count", "manual_seed"]
 
@@ -350,6 +350,23 @@ def _pool_fwd_(emb, pos, mode, out, cnt, argmax):
     _count(1)
 
 
+def _norm_pool_fwd_(x, stats, pos, mode, out, cnt, ysum):
+    lib = _lib.load()
+    b, lmax = pos.shape
+    check(lib.glass_norm_pool_fwd(_p(x), x.stride(0), _p(stats), _p(pos), b, lmax, mode, _p(out), out.stride(0), _p(cnt),
+                                  _p(ysum), x.shape[1], x.shape[0], _stream()), "norm_pool_fwd")
+    _count(1)
+
+
+def _norm_pool_bwd_(dout, pos, mode, cnt, ysum, x, stats, weight, mean_scale, dx, dw, db, dms, scratch):
+    lib = _lib.load()
+    b, lmax = pos.shape
+    check(lib.glass_norm_pool_bwd(_p(dout), dout.stride(0), _p(pos), b, lmax, mode, _p(cnt), _p(ysum), _p(x), x.stride(0),
+                                  _p(stats), _p(weight), _p(mean_scale), _p(dx), dx.stride(0), _p(dw), _p(db), _p(dms),
+                                  x.shape[1], x.shape[0], _p(scratch), scratch.numel(), _stream()), "norm_pool_bwd")
+    _count(2)
+
+
 def _pool_bwd_(dout, pos, mode, cnt, argmax, demb, mark):
     """mark (uint8 [n_node] scratch): deterministic node-centric variant that writes every row of demb."""
     lib = _lib.load()
@@ -364,6 +381,13 @@ _define("segment_pool_fwd_(Tensor emb, Tensor pos, int mode, Tensor(a!) out, Ten
         _pool_fwd_)
 _define("segment_pool_bwd_(Tensor dout, Tensor pos, int mode, Tensor cnt, Tensor? argmax, Tensor(a!) demb, "
         "Tensor(b!)? mark) -> ()", _pool_bwd_)
+
+
+_define("norm_pool_fwd_(Tensor x, Tensor stats, Tensor pos, int mode, Tensor(a!) out, Tensor(b!) cnt, Tensor(c!) ysum) -> ()",
+        _norm_pool_fwd_)
+_define("norm_pool_bwd_(Tensor dout, Tensor pos, int mode, Tensor cnt, Tensor ysum, Tensor x, Tensor stats, Tensor weight, "
+        "Tensor mean_scale, Tensor(a!) dx, Tensor(b!) dw, Tensor(c!) db, Tensor(d!) dms, Tensor(e!) scratch) -> ()",
+        _norm_pool_bwd_)
 
 
 def _pool_batch_fwd_(x, batch, n_seg, mode, out, cnt, argmax):
@@ -1247,6 +1271,59 @@ class _SegmentPoolBatch(torch.autograd.Function):
         dx = torch.empty((m, dout.shape[1]), dtype=torch.float32, device=dout.device)
         _ops.segment_pool_batch_bwd_(dout, batch, n_seg, mode, cnt, argmax, dx)
         return dx, None, None, None
+
+
+NORM_POOL_MODES = ("sum", "mean", "size")
+
+
+class _NormPool(torch.autograd.Function):
+    """pool(GraphNorm(x)[subG_node]) for a GraphNorm whose output feeds only the pooling (the model's last one,
+    impl/models.py:266 / :272 -> :346-350): statistics over all rows, normalisation only on the gathered rows; backward
+    forms the norm's column sums from the pooled gradients and writes dx in one pass (csrc/pool.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mean_scale, eps, pos, mode):
+        x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
+        pos = _req(pos, torch.int64, "subG_node", 2)
+        weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
+        mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
+        n, c = x.shape
+        dev = x.device
+        lib = _lib.load()
+        partial = torch.empty((2 * c, lib.glass_graphnorm_partials_ld()), dtype=torch.float64, device=dev)
+        nblk = graphnorm_partials(x, partial)
+        stats = torch.empty((6, c), dtype=torch.float32, device=dev)
+        _ops.graphnorm_stats_(partial, nblk, n, weight, bias, mean_scale, float(eps), None, 0.0, None, None, stats)
+        b = pos.shape[0]
+        out = torch.empty((b, c), dtype=torch.float32, device=dev)
+        cnt = torch.empty(b, dtype=torch.float32, device=dev)
+        ysum = torch.empty((b, c), dtype=torch.float32, device=dev)
+        _ops.norm_pool_fwd_(x, stats, pos, mode, out, cnt, ysum)
+        ctx.save_for_backward(x, weight, mean_scale, stats, pos, cnt, ysum)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, mean_scale, stats, pos, cnt, ysum = ctx.saved_tensors
+        dout, _ = _rowmajor(dout)
+        n, c = x.shape
+        dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        dw, db, dms = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
+        scratch = torch.empty(_lib.load().glass_segment_pool_bwd_scratch_bytes(pos.shape[0], n), dtype=torch.uint8,
+                              device=x.device)
+        _ops.norm_pool_bwd_(dout, pos, ctx.mode, cnt, ysum, x, stats, weight, mean_scale, dx, dw, db, dms, scratch)
+        return dx, dw, db, dms, None, None, None
+
+
+def graph_norm_pool(x, weight, bias, mean_scale, eps: float, pos: torch.Tensor, mode: str) -> torch.Tensor:
+    """segment_pool(graph_norm(x, weight, bias, mean_scale, eps), pos, mode) as one operator; mode in NORM_POOL_MODES,
+    at most 256 columns."""
+    if mode not in NORM_POOL_MODES:
+        raise NotImplementedError(mode)
+    if x.shape[0] == 0 or x.shape[1] > 256:
+        return segment_pool(graph_norm(x, weight, bias, mean_scale, eps), pos, mode)
+    return _NormPool.apply(x, weight, bias, mean_scale, eps, pos, POOL[mode])
 
 
 def segment_pool_batch(x: torch.Tensor, batch: torch.Tensor, mode: str, size: Optional[int] = None):

@@ -62,6 +62,50 @@ def split_columns_by_owner(rp, c, v, bounds, rebase: bool = True):
     return out
 
 
+MAX_PHASES = int(__import__("os").environ.get("GLASS_B200_PARTITION_PHASES", "4"))
+
+
+def phase_groups(rank: int, world: int, max_phases: int = None):
+    """Source ranks per phase of the pipelined product: [[rank], [rank+1, ...], ...] -- the own shard first, then the
+    peers in arrival order cut into at most max_phases - 1 groups of consecutive sources (every phase walks the row
+    structure and re-reads y once, so eight single-source phases cost more than they hide at world = 8)."""
+    max_phases = MAX_PHASES if max_phases is None else max_phases
+    peers = [(rank + i) % world for i in range(1, world)]
+    groups = [[rank]]
+    k = min(len(peers), max(max_phases - 1, 1))
+    if k:
+        size = -(-len(peers) // k)
+        groups += [peers[i:i + size] for i in range(0, len(peers), size)]
+    return groups
+
+
+def split_columns_by_group(rp, c, v, pad: int, groups):
+    """One CSR per source group: the entries whose column (padded all-gather layout, owner = column // pad) belongs to a
+    source of the group, columns re-based to the group's stage buffer (slot of the source in the group * pad + local
+    row).  Entry order inside a row is kept."""
+    world = sum(len(g) for g in groups)
+    group_of = torch.empty(world, dtype=torch.int64, device=c.device)
+    slot_of = torch.empty(world, dtype=torch.int64, device=c.device)
+    for gi, g in enumerate(groups):
+        for si, src in enumerate(g):
+            group_of[src], slot_of[src] = gi, si
+    n_rows = rp.numel() - 1
+    counts = (rp[1:] - rp[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=c.device), counts)
+    cl = c.long()
+    owner = torch.div(cl, pad, rounding_mode="floor")
+    new_col = (slot_of[owner] * pad + (cl - owner * pad)).to(torch.int32)
+    grp = group_of[owner]
+    out = []
+    for gi in range(len(groups)):
+        sel = grp == gi
+        cnt = torch.bincount(rows[sel], minlength=n_rows)
+        rp_new = torch.zeros(n_rows + 1, dtype=torch.int64, device=c.device)
+        torch.cumsum(cnt, 0, out=rp_new[1:])
+        out.append((rp_new.to(torch.int32), new_col[sel].contiguous(), v[sel].contiguous()))
+    return out
+
+
 def _split_columns(rp, c, v, lo_col: int, hi_col: int):
     """(own, rest): the entries whose column lies in [lo_col, hi_col), re-based to 0, and all others (columns unchanged)."""
     n_rows = rp.numel() - 1
@@ -82,41 +126,43 @@ class PeerExchange:
     """Feature-shard exchange of the pipelined row-partitioned SpMM over NVLink peer memory.
 
     Every rank publishes its [pad, h] shard in a symmetric (peer-mapped) buffer; after one device-side barrier each
-    rank PULLS the peers' shards with copy-engine transfers on side streams, one event per source, in the order
-    rank+1, rank+2, ...  so that the SpMM phase of source s starts as soon as shard s has landed while the other
+    rank PULLS the peers' shards with copy-engine transfers on side streams, one event per source group, in the order
+    rank+1, rank+2, ...  so that the SpMM phase of a group starts as soon as its shards have landed while the other
     transfers are still in flight.  Two buffer generations alternate: a rank may publish the next product's shard
     while slower peers still read the previous one (the barrier of product k+1 proves every pull of product k is
     complete before generation k % 2 is written again).  torch.distributed._symmetric_memory only provides the
     allocation, the address exchange and the barrier; no library collective moves data."""
 
-    def __init__(self, pad: int, h: int, rank: int, world: int, group, device):
+    def __init__(self, pad: int, h: int, rank: int, world: int, group, device, groups):
         import torch.distributed._symmetric_memory as symm_mem
         self.pad, self.h, self.rank, self.world = pad, h, rank, world
         self.group = group if group is not None else dist.group.WORLD
         self.buf = symm_mem.empty((2, pad, h), dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.buf, self.group)
-        self.order = [(rank + i) % world for i in range(1, world)]
-        self.peer = {s: [self.handle.get_buffer(s, (pad, h), torch.float32, g * pad * h) for g in range(2)] for s in self.order}
-        self.stage = {s: torch.empty((pad, h), dtype=torch.float32, device=device) for s in self.order}
-        self.streams = {s: torch.cuda.Stream(device=device) for s in self.order}
+        self.groups = groups[1:]                                   # remote source groups (groups[0] is the own shard)
+        self.peer = {s: [self.handle.get_buffer(s, (pad, h), torch.float32, g * pad * h) for g in range(2)]
+                     for grp in self.groups for s in grp}
+        self.stage = [torch.empty((len(grp) * pad, h), dtype=torch.float32, device=device) for grp in self.groups]
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.groups]
         self.gen = 0
 
     def start(self, send: torch.Tensor):
-        """send [pad, h] (this rank's padded shard).  Returns [(source rank, shard tensor, wait())] own shard first."""
+        """send [pad, h] (this rank's padded shard).  Returns [(stage buffer, wait())] per phase, own shard first."""
         main = torch.cuda.current_stream(send.device)
         g = self.gen
         self.gen ^= 1
         self.buf[g].copy_(send)
         self.handle.barrier(channel=0, timeout_ms=20000)     # every rank's generation-g shard is complete (traps, not hangs)
-        out = [(self.rank, send, lambda: None)]
-        for s in self.order:
-            st = self.streams[s]
-            st.wait_stream(main)                             # after the barrier, and after the last reader of stage[s]
+        out = [(send, lambda: None)]
+        for gi, grp in enumerate(self.groups):
+            st = self.streams[gi]
+            st.wait_stream(main)                             # after the barrier, and after the last reader of this stage
             with torch.cuda.stream(st):
-                self.stage[s].copy_(self.peer[s][g], non_blocking=True)
+                for si, s_ in enumerate(grp):
+                    self.stage[gi][si * self.pad:(si + 1) * self.pad].copy_(self.peer[s_][g], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(st)
-            out.append((s, self.stage[s], (lambda e=ev: main.wait_event(e))))
+            out.append((self.stage[gi], (lambda e=ev: main.wait_event(e))))
         return out
 
 
@@ -158,9 +204,9 @@ class RowPartitionedAdj:
         self.exchange = {}                 # h -> PeerExchange
         self.exchange_override = None      # tests: callable(padded_local) -> [world shards] without peer memory
         if pipelined:
-            bounds = [s_ * self.pad for s_ in range(world + 1)]
-            fwd = split_columns_by_owner(*blk, bounds)
-            bwd = split_columns_by_owner(*blk_t, bounds)
+            self.groups = phase_groups(rank, world)
+            fwd = split_columns_by_group(*blk, self.pad, self.groups)
+            bwd = split_columns_by_group(*blk_t, self.pad, self.groups)
             self.phases = [ops.CSRAdj(self.rows, *f, *b, none, adj.aggr).make_plans() for f, b in zip(fwd, bwd)]
         if overlap:
             lo_col = rank * self.pad
@@ -212,20 +258,21 @@ class RowPartitionedAdj:
         send = self._pad(v_local)
         if self.exchange_override is not None:
             shards = self.exchange_override(send)
-            order = [self.rank] + [(self.rank + i) % self.world for i in range(1, self.world)]
-            arrivals = [(s_, shards[s_], (lambda: None)) for s_ in order]
+            arrivals = [(send, (lambda: None))] + [(torch.cat([shards[s_] for s_ in grp]), (lambda: None))
+                                                   for grp in self.groups[1:]]
         elif self.world == 1:
-            arrivals = [(0, send, (lambda: None))]
+            arrivals = [(send, (lambda: None))]
         else:
             ex = self.exchange.get(h)
             if ex is None:
-                ex = self.exchange[h] = PeerExchange(self.pad, h, self.rank, self.world, self.group, v_local.device)
+                ex = self.exchange[h] = PeerExchange(self.pad, h, self.rank, self.world, self.group, v_local.device,
+                                                     self.groups)
             arrivals = ex.start(send)
         y = torch.empty((self.rows, h), dtype=torch.float32, device=v_local.device)
-        for i, (src, shard, wait) in enumerate(arrivals):
+        for i, (buf, wait) in enumerate(arrivals):
             wait()
-            a = self.phases[src].t() if transposed else self.phases[src]
-            ops._run_spmm(a.rowptr, a.col, a.val, a.plan, shard, y, accumulate=i > 0)
+            a = self.phases[i].t() if transposed else self.phases[i]
+            ops._run_spmm(a.rowptr, a.col, a.val, a.plan, buf, y, accumulate=i > 0)
         return y
 
     def _gather(self, local: torch.Tensor) -> torch.Tensor:

@@ -19,18 +19,13 @@ CONFIG_OF = {"ppi_bp_shaped": "ppi_bp", "em_user_shaped": "em_user", "em_user_sh
 
 
 def load_params(dataset: str) -> dict:
-    """Hyper-parameters of a dataset (GLASSTest.py:273-276).  A reference-style `config/<dataset>.yml` wins if
-    it exists; otherwise the row of `config/hparams.yml`, which holds the reference's values for all datasets."""
+    """Hyper-parameters of a dataset: config/<dataset>.yml, the reference's own files (GLASSTest.py:273-276)."""
     name = CONFIG_OF.get(dataset, dataset)
     own = os.path.join(_CONFIG_DIR, f"{name}.yml")
-    if os.path.exists(own):
-        with open(own) as f:
-            return yaml.safe_load(f)
-    with open(os.path.join(_CONFIG_DIR, "hparams.yml")) as f:
-        table = yaml.safe_load(f)
-    if name not in table:
-        raise FileNotFoundError(f"no hyper-parameters for dataset {dataset!r} (config/hparams.yml or {own})")
-    return dict(table[name])
+    if not os.path.exists(own):
+        raise FileNotFoundError(f"no hyper-parameters for dataset {dataset!r} ({own})")
+    with open(own) as f:
+        return yaml.safe_load(f)
 
 
 def build_model(hidden_dim, conv_layer, dropout, jk, pool, z_ratio, aggr, max_deg, output_channels,

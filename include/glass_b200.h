@@ -297,6 +297,20 @@ int glass_embedding_bwd_ordered(const float* dout, int64_t lddo, const int64_t* 
                                 const int32_t* uid_first_run, const int32_t* uid_runs, int64_t n_uid,
                                 float* run_sum, float* dtable, int64_t rows, int h, void* stream);
 
+/* The model's LAST GraphNorm feeds nothing but the pooling (impl/models.py:266 / :272 -> GLASS.Pool :346-350), so the two
+ * run as one operator on the norm's INPUT x and the statistics table of glass_graphnorm_stats: forward normalises only
+ * the gathered rows (the [n_node, d] output of the norm is never written) and saves ysum[b, :] = sum_v (x_v - am) rstd;
+ * backward writes every row of dx = alpha u + beta yhat + gamma (u = pooled gradient scattered in subgraph order, the
+ * column sums S1 / S2 are formed from the B x d pooled gradients and ysum) and the norm's parameter gradients.
+ * sum / mean / size pooling, d <= 256; scratch as for glass_segment_pool_bwd. */
+int glass_norm_pool_fwd(const float* x, int64_t ldx, const float* stats, const int64_t* pos, int64_t b, int64_t lmax,
+                        int mode, float* out, int64_t ldo, float* cnt, float* ysum, int d, int64_t n_node, void* stream);
+int glass_norm_pool_bwd(const float* dout, int64_t lddo, const int64_t* pos, int64_t b, int64_t lmax, int mode,
+                        const float* cnt, const float* ysum, const float* x, int64_t ldx, const float* stats,
+                        const float* weight, const float* mean_scale, float* dx, int64_t lddx, float* dweight,
+                        float* dbias, float* dmean_scale, int d, int64_t n_node, void* scratch, size_t scratch_bytes,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Padded-subgraph pooling (GLASS.Pool impl/models.py:346-350 = pad2batch + emb[pos] + pool_fn;
  * pools impl/models.py:295-319).  pos int64 [b, lmax], -1 = padding.  One CTA per subgraph reads

@@ -33,7 +33,8 @@ loss_fn(ref_logits.flatten(), y).backward()
 ref = {k: v.grad.detach().clone() for k, v in model.named_parameters()}
 
 adj = model.conv.convs[0].adj
-part = RowPartitionedAdj(adj, rank, world)
+pipelined = os.environ.get('PIPELINED', '0') != '0'
+part = RowPartitionedAdj(adj, rank, world, pipelined=pipelined)
 pm = PartitionedGLASS(model, part)
 model.zero_grad(set_to_none=True)
 h_local = model.conv.input_emb.weight.detach()[part.lo:part.hi].clone().requires_grad_(True)
@@ -84,7 +85,7 @@ def step_repl():
     loss_fn(model(x, ei, ew, pos, z).flatten(), y).backward()
 
 
-out = {"graph": name, "world": world, "n": n, "nnz": int(adj.nnz), "worst_rel_err": float(worst),
+out = {"graph": name, "world": world, "pipelined": pipelined, "n": n, "nnz": int(adj.nnz), "worst_rel_err": float(worst),
        "ms_partitioned_fwd_bwd": timed(step_part), "ms_replicated_fwd_bwd": timed(step_repl),
        "nnz_local": part.nnz_local, "errs_rank0": {k: round(v, 9) for k, v in sorted(errs.items(), key=lambda kv: -kv[1])[:6]}}
 if rank == 0:

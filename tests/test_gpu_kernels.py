@@ -436,9 +436,38 @@ def test_labels_and_pad2batch_known_answers():
     assert torch.equal(b.cpu(), rb) and torch.equal(p.cpu(), rp)
 
 
+@pytest.mark.parametrize("mode", ["sum", "mean", "size"])
+@pytest.mark.parametrize("n,d,b,lmax", [(3000, 64, 6, 40), (777, 17, 5, 9), (5000, 8, 3, 20), (40000, 128, 40, 70)])
+def test_graph_norm_pool_matches_norm_then_pool(mode, n, d, b, lmax):
+    """ops.graph_norm_pool == pool(GraphNorm(x)[subG_node]) of the oracle (impl/models.py:266 -> :346-350), forward and
+    every gradient (x, weight, bias, mean_scale).  Nodes shared by several subgraphs, a node listed twice in one
+    subgraph and an empty subgraph are part of the batch."""
+    from glass_b200 import ops
+    g = torch.Generator().manual_seed(n + d)
+    x = torch.randn(n, d, generator=g) * 2 + torch.randn(1, d, generator=g) * 3
+    w, bias, ms = torch.randn(d, generator=g), torch.randn(d, generator=g), torch.rand(d, generator=g) + 0.5
+    pos = _rand_pad(n, b, lmax, seed=d, empty_row=b - 1)
+    pos[1, :3] = pos[0, :3]                       # nodes shared by two subgraphs
+    pos[2, 1] = pos[2, 0]                         # a node listed twice in one subgraph
+    gout = torch.randn(b, d, generator=g)
+    cpu = [t.clone().requires_grad_(True) for t in (x, w, bias, ms)]
+    batch, nodes = O.pad2batch(pos)
+    ref = O.pool_nodes(O.graph_norm(*cpu)[nodes], batch, mode, b)
+    ref.backward(gout)
+    dev = [t.to(DEV).requires_grad_(True) for t in (x, w, bias, ms)]
+    out = ops.graph_norm_pool(*dev, 1e-5, pos.to(DEV), mode)
+    assert rel_err(out.detach().cpu(), ref.detach()) < 2e-5
+    out.backward(gout.to(DEV))
+    for name, c_, d_ in zip(("x", "weight", "bias", "mean_scale"), cpu, dev):
+        assert rel_err(d_.grad.cpu(), c_.grad) < TOL, name
+    # and bit-for-bit the same pooled values as the two separate operators of the product
+    two = ops.segment_pool(ops.graph_norm(*[t.detach() for t in dev], 1e-5, 0, 0.0, False), pos.to(DEV), mode)
+    assert rel_err(out.detach(), two) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------ row partitioning
 @pytest.mark.parametrize("overlap", [False, True, "pipelined"])
-@pytest.mark.parametrize("world", [1, 3, 4])
+@pytest.mark.parametrize("world", [1, 3, 4, 8])
 def test_row_partitioned_spmm_single_device_emulation(world, overlap):
     """All ranks' blocks built on one GPU; the all-gather is emulated by concatenating the padded shards.
     overlap=True multiplies the locally-owned columns first (while the gather would be in flight); "pipelined" takes
