@@ -257,11 +257,11 @@ class EmbZGConv(nn.Module):
         return self.convs[0].shared_base(self._input(x), edge_index, edge_weight)
 
     @torch.no_grad()
-    def forward_from_base(self, base, edge_index, edge_weight, z=None):
+    def forward_from_base(self, base, edge_index, edge_weight, z=None, pool_to=None):
         n = base[0].shape[0]
         mask = self._mask(n, z, base[0].device)
         return self._layers(None, edge_index, edge_weight, mask,
-                            first=lambda m: self.convs[0].forward_from_base(base, m))
+                            first=lambda m: self.convs[0].forward_from_base(base, m), pool_to=pool_to)
 
 
 # --- pooling --------------------------------------------------------------------------------------
@@ -369,8 +369,12 @@ class GLASS(_SubgraphModel):
     @torch.no_grad()
     def forward_from_base(self, base, edge_index, edge_weight, subG_node, z=None, id=0):
         """model(x, ei, ew, subG_node, z) in evaluation mode with the label-independent work taken from `base`."""
+        pool = self.pools[id]
+        mode = pool.padded_mode() if isinstance(pool, PoolModule) else None
+        if mode in ops.NORM_POOL_MODES and _fuse_norm_pool:        # last GraphNorm + pooling as one operator
+            return self.preds[id](self.conv.forward_from_base(base, edge_index, edge_weight, z, pool_to=(subG_node, mode)))
         emb = self.conv.forward_from_base(base, edge_index, edge_weight, z)
-        return self.preds[id](self.Pool(emb, subG_node, self.pools[id]))
+        return self.preds[id](self.Pool(emb, subG_node, pool))
 
     def Pool(self, emb, subG_node, pool):
         mode = pool.padded_mode() if isinstance(pool, PoolModule) else None
