@@ -175,7 +175,7 @@ def base_line(args, wl, value, ms_per_step):
 
 
 # ------------------------------------------------------------------------------------------ product arm
-def spmm_roofline(adj, h: int, reps: int = 20):
+def spmm_roofline(adj, h: int, reps: int = 20, workload: str = None):
     """Isolated SpMM launches, L2 flushed before each, CUDA events on the launching stream."""
     from glass_b200 import ops
     dev = adj.col.device
@@ -210,7 +210,8 @@ def spmm_roofline(adj, h: int, reps: int = 20):
             digest = hashlib.sha256(f.read()).hexdigest()[:16]
         with open(os.path.join(ROOT, "profiles", "spmm_traffic.json")) as f:
             for t in json.load(f)["captures"]:
-                if t.get("nnz") == adj.nnz and t.get("h") == h and t.get("spmm_cu_sha16") == digest:
+                if (t.get("nnz") == adj.nnz and t.get("h") == h and t.get("spmm_cu_sha16") == digest and
+                        (workload is None or t.get("workload") == workload)):
                     traffic, traffic_note = t["dram_bytes_per_launch"], t.get("source", "")
     except Exception:
         pass
@@ -405,7 +406,7 @@ def run_product(args):
         line["gpu_launches"] = launches
         line["clocks"] = clocks.summary()
         adj = model.conv.convs[0].adj
-        line["roofline"] = spmm_roofline(adj, p["hidden_dim"])
+        line["roofline"] = spmm_roofline(adj, p["hidden_dim"], workload=wl["name"])
         # inference throughput of the same model / batches (impl/train.py:20-34 forward only): one graph per batch,
         # and the multi-label-batch evaluator (adj @ U once per epoch + sparse label correction per batch)
         from glass_b200.graphed import GraphedForward, GraphedSharedBaseForward
@@ -521,7 +522,7 @@ def quick_config(name, dev, steps, warmup, cpu_steps):
            "gpu_launches_per_step": launches, "nodes": int(g.x.shape[0]), "nnz": int(model.conv.convs[0].adj.nnz),
            "hidden_dim": p["hidden_dim"], "conv_layer": p["conv_layer"], "batch_size": p["batch_size"]}
     if name.startswith("em_user"):
-        out["roofline"] = spmm_roofline(model.conv.convs[0].adj, p["hidden_dim"])
+        out["roofline"] = spmm_roofline(model.conv.convs[0].adj, p["hidden_dim"], workload=name)
     if cpu_steps and not name.startswith("em_user"):
         v, per = cpu_port_steps(wl, cpu_steps, 1)
         out["cpu_port"] = {"value": v, "ms_per_step": per * 1e3, "cores": torch.get_num_threads()}

@@ -226,7 +226,7 @@ __global__ void k_pool_pad_bwd(const float* __restrict__ dout, int64_t lddo, Pad
 }
 
 // Deterministic backward of the padded pooling (run-to-run bit-reproducible, SURVEY.md section 5 "Determinism").
-// Node-centric: a warp owns 32 consecutive rows of demb and WRITES all of them (zeros for nodes outside the batch --
+// Node-centric: a warp owns kOrdRows consecutive rows of demb and WRITES all of them (zeros for nodes outside the batch --
 // the caller's zero-fill disappears).  k_mark_nodes builds, per step, a byte mark per node and one membership BITMAP
 // per subgraph (b x ceil(N/32) words); for a marked node the warp reads the node's bit of every subgraph (lane b
 // reads bitmap b) and adds coef_b * dout[b, :] for the subgraphs that list it -- in ascending b, one thread per
@@ -245,6 +245,8 @@ __global__ void k_mark_nodes(const int64_t* __restrict__ pos, int64_t b_cnt, int
 }
 
 constexpr int kOrdWarps = 8;
+constexpr int kOrdRows = 8;     // rows of the gradient a warp owns.  32 rows per warp left 12 warps per SM on the em_user
+                                // shape (1,792 warps in all) for a kernel that is a chain of dependent loads per marked row
 
 // GraphNorm backward fused into the ordered pooling backward (NORM): when the pooled matrix was the output of a
 // GraphNorm that feeds nothing else (PoolNorm above), the gradient with respect to the norm's INPUT is
@@ -307,18 +309,18 @@ k_pool_pad_bwd_ordered(const float* __restrict__ dout, int64_t lddo, const int64
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
-    const int64_t base = ((int64_t)blockIdx.x * kOrdWarps + (threadIdx.x >> 5)) * 32;
+    const int64_t base = ((int64_t)blockIdx.x * kOrdWarps + (threadIdx.x >> 5)) * kOrdRows;
     if (base >= n_node) return;
     const int64_t mine = base + lane;
-    const unsigned labelled = __ballot_sync(0xffffffffu, mine < n_node && mark[mine] != 0);
-    const int rows = (int)min((int64_t)32, n_node - base);
+    const unsigned labelled = __ballot_sync(0xffffffffu, lane < kOrdRows && mine < n_node && mark[mine] != 0);
+    const int rows = (int)min((int64_t)kOrdRows, n_node - base);
     // rows of nodes outside the batch (zeros, or beta * yhat + gamma with NORM) as one coalesced sweep over the warp's
-    // 32-row block when possible
+    // row block when possible
     const bool wide = (d % 4 == 0) && (ldde % 4 == 0) && ((uintptr_t)demb % 16 == 0) &&
                       (!NORM || (nb.ldx % 4 == 0 && (uintptr_t)nb.x % 16 == 0));
     if (wide) {
         const int cv = d >> 2;                                 // float4 per row
-        constexpr int U = NORM ? 8 : 1;                        // NORM: eight row-chunk loads in flight per lane
+        constexpr int U = NORM ? 4 : 1;                        // NORM: four row-chunk loads in flight per lane
         for (int q0 = lane; q0 < rows * cv; q0 += 32 * U) {
             float4 xv[U];
             int jj[U], cc[U];
@@ -486,7 +488,7 @@ extern "C" int glass_segment_pool_bwd(const float* dout, int64_t lddo, const int
         GLASS_CUDA(cudaMemsetAsync(scratch, 0, need, st));
         const int64_t n_pos = b * lmax;
         if (n_pos > 0) k_mark_nodes<<<(unsigned)ceil_div(n_pos, 256), 256, 0, st>>>(pos, b, lmax, mark, memb, words, n_node, dup);
-        k_pool_pad_bwd_ordered<false><<<(unsigned)ceil_div(n_node, kOrdWarps * 32), kOrdWarps * 32, 0, st>>>(
+        k_pool_pad_bwd_ordered<false><<<(unsigned)ceil_div(n_node, kOrdWarps * kOrdRows), kOrdWarps * 32, 0, st>>>(
             dout, lddo, pos, lmax, b, mode, cnt, argmax, mark, memb, words, dup, demb, ldde, d, n_node, NormBwd{});
         GLASS_LAUNCH_CHECK();
         return GLASS_OK;
@@ -543,7 +545,7 @@ extern "C" int glass_norm_pool_bwd(const float* dout, int64_t lddo, const int64_
     const int64_t n_pos = b * lmax;
     if (n_pos > 0) k_mark_nodes<<<(unsigned)ceil_div(n_pos, 256), 256, 0, st>>>(pos, b, lmax, mark, memb, words, n_node, dup);
     NormBwd nb{x, ldx, stats, weight, mean_scale, ysum, dweight, dbias, dmean_scale};
-    k_pool_pad_bwd_ordered<true><<<(unsigned)ceil_div(n_node, kOrdWarps * 32), kOrdWarps * 32, 0, st>>>(
+    k_pool_pad_bwd_ordered<true><<<(unsigned)ceil_div(n_node, kOrdWarps * kOrdRows), kOrdWarps * 32, 0, st>>>(
         dout, lddo, pos, lmax, b, mode, cnt, nullptr, mark, memb, words, dup, dx, lddx, d, n_node, nb);
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;

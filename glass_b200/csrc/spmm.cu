@@ -235,11 +235,11 @@ __global__ void k_spmm_combine(const int32_t* __restrict__ long_row, const int32
 }
 
 // The same sum for widths h = 4 G (G a power of two <= 32) without statistics: one lane group per long row and a float4
-// per lane, four scratch rows in flight, added in chunk order (bit-identical to k_spmm_combine).  The column-per-thread
+// per lane, up to sixteen scratch rows in flight, added in chunk order (bit-identical to k_spmm_combine).  The column-per-thread
 // kernel above walks 16 long rows per CTA one after the other on h threads: 14 us for the 2,345 split rows of the
 // power-law em_user-shaped graph.
 template <int G>
-__global__ void __launch_bounds__(kThreads) k_spmm_combine_vec(const int32_t* __restrict__ long_row,
+__global__ void __launch_bounds__(kThreads, 2) k_spmm_combine_vec(const int32_t* __restrict__ long_row,
                                                                const int32_t* __restrict__ long_slot,
                                                                const int32_t* __restrict__ long_cnt, int64_t n_long,
                                                                const float* __restrict__ scratch, int64_t ld_s, float* y,
@@ -252,6 +252,16 @@ __global__ void __launch_bounds__(kThreads) k_spmm_combine_vec(const int32_t* __
         const float4* src = reinterpret_cast<const float4*>(scratch + (int64_t)s0 * ld_s) + l;
         const int64_t step = ld_s >> 2;
         int k = 0;
+        // sixteen scratch rows in flight: the longest row of the power-law em_user-shaped graph has 107 chunks, and
+        // with four loads per round trip its 27 dependent round trips WERE the kernel (22 us for 2.4 MB)
+        for (; k + 16 <= cnt; k += 16) {
+            float4 t[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) t[u] = __ldg(src + (int64_t)(k + u) * step);
+            asm volatile("" ::: "memory");     // all sixteen loads are issued before the first (ordered) add
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc.x += t[u].x, acc.y += t[u].y, acc.z += t[u].z, acc.w += t[u].w;
+        }
         for (; k + 4 <= cnt; k += 4) {
             const float4 a = __ldg(src + (int64_t)k * step), b = __ldg(src + (int64_t)(k + 1) * step);
             const float4 c = __ldg(src + (int64_t)(k + 2) * step), d = __ldg(src + (int64_t)(k + 3) * step);

@@ -305,3 +305,46 @@ def test_real_dataset_loader_equals_the_reference_loader(tmp_path, monkeypatch, 
     assert torch.equal(mine.pos, ref.pos) and torch.equal(mine.y, ref.y)
     assert torch.equal(mine.mask.to(ref.mask.dtype), ref.mask)
     assert mine.x.shape == ref.x.shape
+
+
+# ------------------------------------------------------------------------------------------ row partition host logic
+def test_partition_phase_groups_and_column_split():
+    """glass_b200.partition: the pipelined product takes the own shard first and the peers in arrival order in at
+    most `max_phases` groups; split_columns_by_group re-bases the columns of every group to its stage buffer and
+    keeps every entry exactly once, in row order."""
+    from glass_b200.partition import phase_groups, split_columns_by_group, split_columns_by_owner
+    for world in (1, 2, 3, 4, 8, 16):
+        for rank in (0, world - 1):
+            g = phase_groups(rank, world, 4)
+            assert g[0] == [rank] and len(g) <= 4
+            flat = [s_ for grp in g for s_ in grp]
+            assert sorted(flat) == list(range(world))
+            assert flat[1:] == [(rank + i) % world for i in range(1, world)]        # arrival order
+    assert phase_groups(0, 8, 4) == [[0], [1, 2, 3], [4, 5, 6], [7]]
+    assert phase_groups(5, 8, 2) == [[5], [6, 7, 0, 1, 2, 3, 4]]
+    # a 4-row block whose columns live in a padded layout of 3 owners x pad 4
+    rp = torch.tensor([0, 3, 5, 5, 9], dtype=torch.int32)
+    c = torch.tensor([0, 5, 9, 2, 3, 1, 4, 8, 11], dtype=torch.int32)
+    v = torch.arange(9, dtype=torch.float32)
+    groups = [[1], [2, 0]]                                     # rank 1 of 3: own, then 2 and 0 in one group
+    parts = split_columns_by_group(rp, c, v, 4, groups)
+    (rp0, c0, v0), (rp1, c1, v1) = parts
+    assert rp0.tolist() == [0, 1, 1, 1, 2] and c0.tolist() == [1, 0] and v0.tolist() == [1.0, 6.0]
+    # owner 2 -> slot 0 (columns 8..11 -> 0..3), owner 0 -> slot 1 (columns 0..3 -> 4..7)
+    assert rp1.tolist() == [0, 2, 4, 4, 7] and c1.tolist() == [4, 1, 6, 7, 5, 0, 3] and v1.tolist() == [0., 2., 3., 4., 5., 7., 8.]
+    by_owner = split_columns_by_owner(rp, c, v, [0, 4, 8, 12])
+    assert [p[1].tolist() for p in by_owner] == [[0, 2, 3, 1], [1, 0], [1, 0, 3]]
+    assert sum(int(p[0][-1]) for p in by_owner) == 9
+
+
+def test_dp_owned_ranges_cover_the_table():
+    """glass_b200.dp.owned_range: contiguous, multiples of 4, disjoint, covering -- every element of the table is reduced
+    and updated by exactly one rank."""
+    from glass_b200.dp import owned_range
+    for n in (4, 64, 57333 * 64, 17080 * 64, 1000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [owned_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(lo % 4 == 0 for lo, _ in spans)
