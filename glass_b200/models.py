@@ -232,8 +232,9 @@ class EmbZGConv(nn.Module):
                 h = self.gns[layer](h, act=act, p=self.dropout, training=self.training)
         last = self.gns[-1]
         if self.jk and len(xs) > 1:                                                         # :263-267
-            emb = ops.graph_norm_cat(xs, last.weight, last.bias, last.mean_scale, last.eps)
-            return emb if pool_to is None else ops.segment_pool(emb, *pool_to)
+            if pool_to is not None:
+                return ops.graph_norm_pool_cat(xs, last.weight, last.bias, last.mean_scale, last.eps, *pool_to)
+            return ops.graph_norm_cat(xs, last.weight, last.bias, last.mean_scale, last.eps)
         if pool_to is not None:
             return ops.graph_norm_pool(xs[-1], last.weight, last.bias, last.mean_scale, last.eps, *pool_to)
         return last(xs[-1])                                                                 # :268-272

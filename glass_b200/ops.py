@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, AGGR, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, POOL, check
 
-__all__ = ["CSRAdj", "build_csr", "to_undirected", "spmm", "spmm_graph_norm", "graph_norm_pool", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
+__all__ = ["CSRAdj", "build_csr", "to_undirected", "spmm", "spmm_graph_norm", "graph_norm_pool", "graph_norm_pool_cat", "glass_conv", "conv_fusable", "pair_linear_mix", "graph_norm", "graph_norm_cat", "embedding",
            "segment_pool", "segment_pool_batch", "maxzoz", "label_mask", "pad2batch", "inject_keep_masks",
            "set_gemm_path", "launch_count", "reset_launch_count", "manual_seed"]
 
@@ -1314,6 +1314,70 @@ class _NormPool(torch.autograd.Function):
                               device=x.device)
         _ops.norm_pool_bwd_(dout, pos, ctx.mode, cnt, ysum, x, stats, weight, mean_scale, dx, dw, db, dms, scratch)
         return dx, dw, db, dms, None, None, None
+
+
+class _NormPoolCat(torch.autograd.Function):
+    """_NormPool over the COLUMN BLOCKS of a virtual concat (the JK case, impl/models.py:263-267: the last GraphNorm spans
+    cat(xs) and GraphNorm is per column, so block l is normalised with the parameter slice [off_l, off_l + w_l) and pooled
+    into the same columns of the output).  One autograd node: no parameter slicing / gradient re-assembly kernels."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, mean_scale, eps, pos, mode, *xs):
+        pos = _req(pos, torch.int64, "subG_node", 2)
+        weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
+        mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
+        xs = [_rowmajor(_req(x, torch.float32, "x", 2))[0] for x in xs]
+        n, dev = xs[0].shape[0], xs[0].device
+        d_total = sum(x.shape[1] for x in xs)
+        lib = _lib.load()
+        b = pos.shape[0]
+        out = torch.empty((b, d_total), dtype=torch.float32, device=dev)
+        cnt = torch.empty(b, dtype=torch.float32, device=dev)
+        saved, off = [], 0
+        for x in xs:
+            c = x.shape[1]
+            partial = torch.empty((2 * c, lib.glass_graphnorm_partials_ld()), dtype=torch.float64, device=dev)
+            nblk = graphnorm_partials(x, partial)
+            stats = torch.empty((6, c), dtype=torch.float32, device=dev)
+            _ops.graphnorm_stats_(partial, nblk, n, weight[off:off + c], bias[off:off + c], mean_scale[off:off + c],
+                                  float(eps), None, 0.0, None, None, stats)
+            ysum = torch.empty((b, c), dtype=torch.float32, device=dev)
+            _ops.norm_pool_fwd_(x, stats, pos, mode, out[:, off:off + c], cnt, ysum)
+            saved += [x, stats, ysum]
+            off += c
+        ctx.save_for_backward(weight, mean_scale, pos, cnt, *saved)
+        ctx.mode, ctx.n_blocks = mode, len(xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        weight, mean_scale, pos, cnt = ctx.saved_tensors[:4]
+        rest = ctx.saved_tensors[4:]
+        dout, _ = _rowmajor(dout)
+        dw, db, dms = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
+        lib = _lib.load()
+        dxs, off = [], 0
+        for i in range(ctx.n_blocks):
+            x, stats, ysum = rest[3 * i:3 * i + 3]
+            n, c = x.shape
+            dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+            scratch = torch.empty(lib.glass_segment_pool_bwd_scratch_bytes(pos.shape[0], n), dtype=torch.uint8, device=x.device)
+            _ops.norm_pool_bwd_(dout[:, off:off + c], pos, ctx.mode, cnt, ysum, x, stats, weight[off:off + c],
+                                mean_scale[off:off + c], dx, dw[off:off + c], db[off:off + c], dms[off:off + c], scratch)
+            dxs.append(dx)
+            off += c
+        return (dw, db, dms, None, None, None, *dxs)
+
+
+def graph_norm_pool_cat(xs, weight, bias, mean_scale, eps: float, pos: torch.Tensor, mode: str) -> torch.Tensor:
+    """segment_pool(graph_norm(cat(xs, -1), ...), pos, mode) without the concat, the normalised matrix or the pooled
+    gradient matrix; mode in NORM_POOL_MODES, every block at most 256 columns wide."""
+    if mode not in NORM_POOL_MODES:
+        raise NotImplementedError(mode)
+    xs = list(xs)
+    if xs[0].shape[0] == 0 or max(x.shape[1] for x in xs) > 256:
+        return segment_pool(graph_norm_cat(xs, weight, bias, mean_scale, eps), pos, mode)
+    return _NormPoolCat.apply(weight, bias, mean_scale, eps, pos, POOL[mode], *xs)
 
 
 def graph_norm_pool(x, weight, bias, mean_scale, eps: float, pos: torch.Tensor, mode: str) -> torch.Tensor:

@@ -465,6 +465,32 @@ def test_graph_norm_pool_matches_norm_then_pool(mode, n, d, b, lmax):
     assert rel_err(out.detach(), two) < 1e-6
 
 
+@pytest.mark.parametrize("mode", ["sum", "mean", "size"])
+@pytest.mark.parametrize("widths", [(64, 64), (20, 20), (8, 32, 16)])
+def test_graph_norm_pool_cat_matches_norm_of_concat_then_pool(mode, widths):
+    """ops.graph_norm_pool_cat == pool(GraphNorm(cat(xs))[subG_node]) (the JK case, impl/models.py:263-267 -> :346-350):
+    forward and the gradients of every block and of the norm's parameters, against the oracle."""
+    from glass_b200 import ops
+    n, b, lmax = 2500, 7, 30
+    g = torch.Generator().manual_seed(sum(widths))
+    d = sum(widths)
+    xs = [torch.randn(n, w_, generator=g) * 2 + torch.randn(1, w_, generator=g) for w_ in widths]
+    w, bias, ms = torch.randn(d, generator=g), torch.randn(d, generator=g), torch.rand(d, generator=g) + 0.5
+    pos = _rand_pad(n, b, lmax, seed=d, empty_row=b - 1)
+    pos[1, :3] = pos[0, :3]
+    gout = torch.randn(b, d, generator=g)
+    cpu = [t.clone().requires_grad_(True) for t in (*xs, w, bias, ms)]
+    batch, nodes = O.pad2batch(pos)
+    ref = O.pool_nodes(O.graph_norm(torch.cat(cpu[:len(xs)], -1), *cpu[len(xs):])[nodes], batch, mode, b)
+    ref.backward(gout)
+    dev = [t.to(DEV).requires_grad_(True) for t in (*xs, w, bias, ms)]
+    out = ops.graph_norm_pool_cat(dev[:len(xs)], *dev[len(xs):], 1e-5, pos.to(DEV), mode)
+    assert rel_err(out.detach().cpu(), ref.detach()) < 2e-5
+    out.backward(gout.to(DEV))
+    for i, (c_, d_) in enumerate(zip(cpu, dev)):
+        assert rel_err(d_.grad.cpu(), c_.grad) < TOL, i
+
+
 # ------------------------------------------------------------------------------------------ row partitioning
 @pytest.mark.parametrize("overlap", [False, True, "pipelined"])
 @pytest.mark.parametrize("world", [1, 3, 4, 8])

@@ -49,6 +49,8 @@ def oracle_ops(monkeypatch):
     monkeypatch.setattr(ops, "graph_norm_cat", lambda xs, w, b, a, eps=1e-5: O.graph_norm(torch.cat(list(xs), -1), w, b, a, eps))
     monkeypatch.setattr(ops, "graph_norm_pool", lambda x, w, b, a, eps, pos, mode:
                         _segment_pool(O.graph_norm(x, w, b, a, eps), pos, mode))
+    monkeypatch.setattr(ops, "graph_norm_pool_cat", lambda xs, w, b, a, eps, pos, mode:
+                        _segment_pool(O.graph_norm(torch.cat(list(xs), -1), w, b, a, eps), pos, mode))
     monkeypatch.setattr(ops, "label_mask", lambda z: (z > 0.5).to(torch.uint8))
     monkeypatch.setattr(ops, "embedding", lambda ids, table: table[ids])
     monkeypatch.setattr(ops, "segment_pool", _segment_pool)
