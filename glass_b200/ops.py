@@ -1276,50 +1276,13 @@ class _SegmentPoolBatch(torch.autograd.Function):
 NORM_POOL_MODES = ("sum", "mean", "size")
 
 
-class _NormPool(torch.autograd.Function):
-    """pool(GraphNorm(x)[subG_node]) for a GraphNorm whose output feeds only the pooling (the model's last one,
-    impl/models.py:266 / :272 -> :346-350): statistics over all rows, normalisation only on the gathered rows; backward
-    forms the norm's column sums from the pooled gradients and writes dx in one pass (csrc/pool.cu)."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, mean_scale, eps, pos, mode):
-        x, _ = _rowmajor(_req(x, torch.float32, "x", 2))
-        pos = _req(pos, torch.int64, "subG_node", 2)
-        weight, bias = _req(weight, torch.float32, "weight", 1), _req(bias, torch.float32, "bias", 1)
-        mean_scale = _req(mean_scale, torch.float32, "mean_scale", 1)
-        n, c = x.shape
-        dev = x.device
-        lib = _lib.load()
-        partial = torch.empty((2 * c, lib.glass_graphnorm_partials_ld()), dtype=torch.float64, device=dev)
-        nblk = graphnorm_partials(x, partial)
-        stats = torch.empty((6, c), dtype=torch.float32, device=dev)
-        _ops.graphnorm_stats_(partial, nblk, n, weight, bias, mean_scale, float(eps), None, 0.0, None, None, stats)
-        b = pos.shape[0]
-        out = torch.empty((b, c), dtype=torch.float32, device=dev)
-        cnt = torch.empty(b, dtype=torch.float32, device=dev)
-        ysum = torch.empty((b, c), dtype=torch.float32, device=dev)
-        _ops.norm_pool_fwd_(x, stats, pos, mode, out, cnt, ysum)
-        ctx.save_for_backward(x, weight, mean_scale, stats, pos, cnt, ysum)
-        ctx.mode = mode
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        x, weight, mean_scale, stats, pos, cnt, ysum = ctx.saved_tensors
-        dout, _ = _rowmajor(dout)
-        n, c = x.shape
-        dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
-        dw, db, dms = torch.empty_like(weight), torch.empty_like(weight), torch.empty_like(weight)
-        scratch = torch.empty(_lib.load().glass_segment_pool_bwd_scratch_bytes(pos.shape[0], n), dtype=torch.uint8,
-                              device=x.device)
-        _ops.norm_pool_bwd_(dout, pos, ctx.mode, cnt, ysum, x, stats, weight, mean_scale, dx, dw, db, dms, scratch)
-        return dx, dw, db, dms, None, None, None
-
-
 class _NormPoolCat(torch.autograd.Function):
-    """_NormPool over the COLUMN BLOCKS of a virtual concat (the JK case, impl/models.py:263-267: the last GraphNorm spans
-    cat(xs) and GraphNorm is per column, so block l is normalised with the parameter slice [off_l, off_l + w_l) and pooled
-    into the same columns of the output).  One autograd node: no parameter slicing / gradient re-assembly kernels."""
+    """pool(GraphNorm(cat(xs))[subG_node]) for a GraphNorm whose output feeds only the pooling (the model's last one,
+    impl/models.py:266 / :272 -> :346-350): statistics over all rows, normalisation only on the gathered rows; backward
+    forms the norm's column sums from the pooled gradients and writes dx in one pass (csrc/pool.cu).  xs are the COLUMN
+    BLOCKS of a virtual concat (JK, :263-267; one block otherwise): GraphNorm is per column, so block l is normalised
+    with the parameter slice [off_l, off_l + w_l) and pooled into the same columns of the output.  One autograd node:
+    no parameter slicing / gradient re-assembly kernels."""
 
     @staticmethod
     def forward(ctx, weight, bias, mean_scale, eps, pos, mode, *xs):
@@ -1381,13 +1344,9 @@ def graph_norm_pool_cat(xs, weight, bias, mean_scale, eps: float, pos: torch.Ten
 
 
 def graph_norm_pool(x, weight, bias, mean_scale, eps: float, pos: torch.Tensor, mode: str) -> torch.Tensor:
-    """segment_pool(graph_norm(x, weight, bias, mean_scale, eps), pos, mode) as one operator; mode in NORM_POOL_MODES,
-    at most 256 columns."""
-    if mode not in NORM_POOL_MODES:
-        raise NotImplementedError(mode)
-    if x.shape[0] == 0 or x.shape[1] > 256:
-        return segment_pool(graph_norm(x, weight, bias, mean_scale, eps), pos, mode)
-    return _NormPool.apply(x, weight, bias, mean_scale, eps, pos, POOL[mode])
+    """segment_pool(graph_norm(x, weight, bias, mean_scale, eps), pos, mode) as one operator (the single-block case of
+    graph_norm_pool_cat); mode in NORM_POOL_MODES, at most 256 columns."""
+    return graph_norm_pool_cat([x], weight, bias, mean_scale, eps, pos, mode)
 
 
 def segment_pool_batch(x: torch.Tensor, batch: torch.Tensor, mode: str, size: Optional[int] = None):

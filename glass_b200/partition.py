@@ -15,6 +15,7 @@ layout.  GEMMs, label mix, pooling gathers are row-local and need no communicati
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -62,7 +63,7 @@ def split_columns_by_owner(rp, c, v, bounds, rebase: bool = True):
     return out
 
 
-MAX_PHASES = int(__import__("os").environ.get("GLASS_B200_PARTITION_PHASES", "4"))
+MAX_PHASES = int(os.environ.get("GLASS_B200_PARTITION_PHASES", "4"))
 
 
 def phase_groups(rank: int, world: int, max_phases: int = None):
