@@ -33,8 +33,8 @@ errors of the difference (coreness, in this repo's favour and towards the paper'
 other way, 0.875 against 0.880, so this is read as seed noise on one fixed 55-subgraph test split, not as a defect of the
 reference or a gain of this repo); 30 seeds resolve about 0.8 pt on these 55-63-subgraph test splits (one flipped prediction =
 1.6-1.8 pt), so the 0.5 pt bar of the north star can only be met statistically, not seed by seed -- which `--use_one` makes
-impossible for any two implementations (DESIGN.md section 2, "Degenerate `--use_one` inputs").  The CPU columns hold as many
-repeats as the reference finished inside the round (46-212 s per run on 2 threads).  Logs: `r02/glasstest_repeat30_*.log`,
+impossible for any two implementations (DESIGN.md section 2, "Degenerate `--use_one` inputs").  The CPU columns are the unmodified
+reference run in the build container (46-202 s per run on 2 threads, `PYTHONPATH=oracle/pyg_shim`).  Logs: `r02/glasstest_repeat30_*.log`,
 `r02/reference_cpu_repeat30_*.log`; `python scripts/score_table.py` rewrites this table from them."""
 p = os.path.join(ROOT, "profiles", "README.md")
 s = open(p).read()
