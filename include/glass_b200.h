@@ -131,6 +131,11 @@ int glass_spmm_csr_acc(const int32_t* rowptr, const int32_t* col, const float* v
 int glass_l2_gather_probe(const float* x, int64_t ldx, int64_t n_rows, int h, int64_t gathers, float* sink,
                           int64_t sink_elems, void* stream);
 
+/* Measurement aid: the same gathers from a 24-bit two-plane copy of x (hi: top 16 bits, lo: next 8 mantissa bits of every
+ * fp32; convert != 0 fills the planes from x first).  What a reduced gather format would buy the L2-bound SpMM. */
+int glass_l2_gather_probe24(const float* x, int64_t n_rows, int h, int64_t gathers, uint16_t* hi, uint8_t* lo,
+                            float* sink, int64_t sink_elems, int convert, void* stream);
+
 /* Sparse label correction for multi-label-batch evaluation (reference
  * impl/train.py:20-34 evaluates every label batch with a full adj @ x).  For fixed weights the mixed features of two
  * label batches differ only on the labelled rows (impl/models.py:161-162): x_b = U + [mask] * delta, hence
