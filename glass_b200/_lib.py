@@ -71,6 +71,7 @@ PROTOTYPES = {
     "glass_spmm_csr_acc": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp,
                                   _vp, _i64, _vp, _i32, _vp]),
     "glass_l2_gather_probe": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _i64, _vp]),
+    "glass_l2_gather_probe256": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _i64, _i32, _vp]),
     "glass_l2_gather_probe24": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "glass_embedding_fwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "glass_embedding_bwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),

@@ -47,6 +47,37 @@ __global__ void __launch_bounds__(kThreads, 5) k_l2_gather_probe24(const uint16_
     sink[(int64_t)blockIdx.x * kThreads + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
 }
 
+// fp32 rows gathered with 256-bit loads: G lanes x 32 bytes per row (h = 8 G), half the load instructions of the
+// float4 layout for the same bytes.
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+template <int G, int U>
+__global__ void __launch_bounds__(kThreads, 4) k_l2_gather_probe256(const float* __restrict__ x, uint32_t ldx, uint32_t n_rows,
+                                                                  int64_t per_group, float* __restrict__ sink) {
+    const int lane = threadIdx.x & 31, l = lane & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+    uint32_t s = (uint32_t)group * 2654435761u + 12345u;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = 0; i < per_group; i += U) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s = s * 1664525u + 1013904223u;
+            const uint32_t r = (uint32_t)(((uint64_t)s * n_rows) >> 32);
+            ldg256(x + (size_t)r * ldx + 8 * l, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[u][k];
+    }
+    sink[(int64_t)blockIdx.x * kThreads + threadIdx.x] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+
 }  // namespace
 }  // namespace glass
 
@@ -71,6 +102,27 @@ extern "C" int glass_l2_gather_probe24(const float* x, int64_t n_rows, int h, in
     if (g == 8) k_l2_gather_probe24<8><<<(unsigned)grid, kThreads, 0, st>>>(hi, lo, (uint32_t)h, (uint32_t)n_rows, per_group, sink);
     else if (g == 16) k_l2_gather_probe24<16><<<(unsigned)grid, kThreads, 0, st>>>(hi, lo, (uint32_t)h, (uint32_t)n_rows, per_group, sink);
     else k_l2_gather_probe24<32><<<(unsigned)grid, kThreads, 0, st>>>(hi, lo, (uint32_t)h, (uint32_t)n_rows, per_group, sink);
+    GLASS_LAUNCH_CHECK();
+    return GLASS_OK;
+}
+
+// The fp32 probe with 256-bit loads (h in {64, 128, 256}: h / 8 lanes per row, rows 32-byte aligned); `unroll` in {4, 8}.
+extern "C" int glass_l2_gather_probe256(const float* x, int64_t ldx, int64_t n_rows, int h, int64_t gathers, float* sink,
+                                        int64_t sink_elems, int unroll, void* stream) {
+    GLASS_CHECK_ARG(x && sink && n_rows > 0 && gathers > 0 && (h == 64 || h == 128 || h == 256) && ldx >= h && ldx % 8 == 0 &&
+                        (uintptr_t)x % 32 == 0 && n_rows * ldx < (1ll << 31) && (unroll == 4 || unroll == 8),
+                    "l2_gather_probe256: bad arguments");
+    const int g = h / 8;
+    const int64_t grid = (int64_t)sm_count() * 4;
+    GLASS_CHECK_ARG(sink_elems >= grid * kThreads, "l2_gather_probe256: sink needs %lld floats", (long long)(grid * kThreads));
+    const int64_t groups = grid * kThreads / g;
+    const int64_t per_group = (ceil_div(gathers, groups) + 7) / 8 * 8;
+    cudaStream_t st = as_stream(stream);
+#define GO(G, U) k_l2_gather_probe256<G, U><<<(unsigned)grid, kThreads, 0, st>>>(x, (uint32_t)ldx, (uint32_t)n_rows, per_group, sink)
+    if (g == 8) { if (unroll == 8) GO(8, 8); else GO(8, 4); }
+    else if (g == 16) { if (unroll == 8) GO(16, 8); else GO(16, 4); }
+    else { if (unroll == 8) GO(32, 8); else GO(32, 4); }
+#undef GO
     GLASS_LAUNCH_CHECK();
     return GLASS_OK;
 }

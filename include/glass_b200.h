@@ -136,6 +136,10 @@ int glass_l2_gather_probe(const float* x, int64_t ldx, int64_t n_rows, int h, in
 int glass_l2_gather_probe24(const float* x, int64_t n_rows, int h, int64_t gathers, uint16_t* hi, uint8_t* lo,
                             float* sink, int64_t sink_elems, int convert, void* stream);
 
+/* Measurement aid: the fp32 gather probe with 256-bit loads (h / 8 lanes per row instead of h / 4). */
+int glass_l2_gather_probe256(const float* x, int64_t ldx, int64_t n_rows, int h, int64_t gathers, float* sink,
+                             int64_t sink_elems, int unroll, void* stream);
+
 /* Sparse label correction for multi-label-batch evaluation (reference
  * impl/train.py:20-34 evaluates every label batch with a full adj @ x).  For fixed weights the mixed features of two
  * label batches differ only on the labelled rows (impl/models.py:161-162): x_b = U + [mask] * delta, hence

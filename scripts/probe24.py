@@ -36,4 +36,7 @@ torch.cuda.synchronize()
 rel = float((got.double() - ref.double()).abs().max() / ref.double().abs().max())
 out = {"fp32_us": timeit(p32), "split24_us": timeit(lambda: p24(0)), "split24_with_conversion_us": timeit(lambda: p24(1)),
        "sum_rel_diff": rel, "bytes_fp32": gathers * 4 * h, "bytes_24": gathers * 3 * h}
+for u in (4, 8):
+    p256 = lambda u=u: _lib.check(lib.glass_l2_gather_probe256(vp(x), x.stride(0), n, h, gathers, vp(sink), sink.numel(), u, None), "probe256")
+    out[f"fp32_256bit_loads_unroll{u}_us"] = timeit(p256)
 print(json.dumps(out))
